@@ -1,0 +1,61 @@
+// LATER.h - C++-linkage entry points of the RGSQRF path, signature-compatible with the reference
+// header of the same name (reference include/LATER.h:19-22, :39-47, :104-110, :140-154, :213-222)
+// so that the reference's own test/test_qr.cu compiles and links against this library unchanged.
+// Only the symbols that driver needs are declared; everything is a thin wrapper over the C ABI in
+// later_b200.h.  Matrices are column-major fp32 on the device.
+#pragma once
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cublas_v2.h>   // only for the handle types inside cudaCtxt; no cuBLAS call is made
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <curand.h>
+#include <cusolverDn.h>
+
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+
+// Passed BY VALUE by callers (reference include/LATER.h:19-22).  The handles are not used by this
+// implementation; work runs on the legacy default stream, which is the stream the handles of the
+// reference driver are bound to, so the caller's event timers bracket it the same way.
+struct cudaCtxt {
+    cublasHandle_t cublas_handle;
+    cusolverDnHandle_t cusolver_handle;
+};
+
+// A = Q R, A (m x n, lda == m) overwritten by explicit Q, R (n x n) upper triangular.
+// work / hwork are accepted for source compatibility and ignored (internal stream-ordered arena).
+void later_rgsqrf(cudaCtxt ctxt, int m, int n, float* A, int lda, float* R, int ldr, float* work,
+                  int lwork, __half* hwork, int lhwork);
+
+// Explicit Q = I - W Y^T from a Householder WY pair (reference QR/later_ormqr.cu:18-85).
+void later_ormqr(int m, int n, float* W, int ldw, float* Y, int ldy, float* work);
+void later_ormqr2(int m, int n, float* W, int ldw, float* Y, int ldy, float* work);
+
+// Householder QR variants are OUT OF SCOPE of this library: these exist only so
+// the reference driver links; calling them prints a message and exits with status 2.
+void later_rhouqr(cudaCtxt ctxt, int m, int n, float* A, int lda, float* W, int ldw, float* R,
+                  int ldr, float* work, int lwork, __half* hwork, int lhwork, float* U);
+void later_bhouqr(int m, int n, float* A, int lda, float* W, int ldw, float* R, int ldr,
+                  float* work, int lwork, __half* hwork, int lhwork, float* U);
+
+// Utilities the reference driver calls (reference util/util.cu).
+void startTimer();
+float stopTimer();                                   // milliseconds since startTimer()
+void generateUniformMatrix(float* dA, int m, int n); // cuRAND XORWOW, seed 3000, U(0,1]
+void generateNormalMatrix(float* dA, int m, int n);
+float snorm(int m, int n, float* dA);                // Frobenius norm of m*n contiguous floats
+void print_env();
+
+__global__ void s2h(int m, int n, float* as, int ldas, __half* ah, int ldah);
+__global__ void h2s(int m, int n, __half* ah, int ldah, float* as, int ldas);
+__global__ void setEye(int m, int n, float* a, int lda);
+__global__ void clearTri(char uplo, int m, int n, float* a, int lda);

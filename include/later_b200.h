@@ -1,0 +1,93 @@
+/* later_b200.h - C ABI of the B200-native RGSQRF path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  Every matrix is
+ * column-major fp32 exactly as in the reference's include/LATER.h (A is m x n with leading
+ * dimension lda, R is n x n with leading dimension ldr).  The C++-linkage LATER.h entry points
+ * (include/LATER.h in this repo) are one-line wrappers over these functions.
+ *
+ * All functions return 0 on success, a positive cudaError_t value for CUDA failures and a negative
+ * LATER_B200_E* value for argument errors; later_b200_last_error() gives a message.  Nothing throws
+ * across this boundary.  A context is bound to one device and one stream; calls on one context must
+ * come from one host thread at a time (the reference is not re-entrant either: global timer events,
+ * reference util/util.cu:4-22).
+ */
+#ifndef LATER_B200_H
+#define LATER_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct later_b200_ctx later_b200_ctx;
+
+enum {
+    LATER_B200_OK = 0,
+    LATER_B200_EINVAL = -1,   /* bad shape / pointer / leading dimension */
+    LATER_B200_ENOMEM = -2,   /* workspace could not be obtained */
+    LATER_B200_ESTATE = -3,   /* call sequence error (e.g. tsqr_apply without a factorisation) */
+    LATER_B200_ENODEV = -4    /* no sm_100 device */
+};
+
+/* Creates a context on `device`.  `stream` is a cudaStream_t (may be NULL = legacy default stream,
+ * which is what the reference runs on: reference QR/later_rgsqrf.cu has no stream anywhere). */
+int later_b200_create(later_b200_ctx** out, int device, void* stream);
+int later_b200_destroy(later_b200_ctx* ctx);
+const char* later_b200_last_error(const later_b200_ctx* ctx);
+
+/* 1 = replay the factorisation from a cached CUDA graph (default), 0 = plain stream launches. */
+int later_b200_set_graph(later_b200_ctx* ctx, int enable);
+
+/* Bytes of internal workspace later_b200_rgsqrf(m, n) needs (fp16 shadow of A, fp16 R12, split-K
+ * partials, panel scratch).  The context allocates it itself, stream-ordered; this is for sizing. */
+size_t later_b200_workspace_bytes(const later_b200_ctx* ctx, int m, int n);
+
+/* Recursive Gram-Schmidt QR.  Replaces later_rgsqrf (reference include/LATER.h:39,
+ * QR/later_rgsqrf.cu:62-79).  In: A (device, m x n, lda >= m).  Out: A <- explicit Q,
+ * R <- upper-triangular factor (the whole strictly lower triangle is written as zero).
+ * Requirements: m >= n, n a multiple of 128, m a multiple of 8. */
+int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr);
+
+/* Same with HOST buffers: copies A to the device, factors, copies Q and R back (end-to-end path
+ * used by bench.py's e2e figure). */
+int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda, float* hR,
+                           int ldr);
+
+/* 128-column tall-skinny panel only (reference mgs_caqr_panel_256x128, QR/panel.cu:10-63).
+ * n must be 128.  Qh (optional, device fp16, leading dimension ldqh) receives the fp16 copy. */
+int later_b200_panel_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr);
+
+/* TSQR back-multiplication for the row-sharded multi-GPU factorisation: Q <- Qh * W, where Qh is
+ * the fp16 shadow of the Q most recently produced by later_b200_rgsqrf on this context (same m, n,
+ * Q pointer) and W (device, n x n fp32) is this rank's block of the stacked-R factor's Q. */
+int later_b200_tsqr_apply(later_b200_ctx* ctx, int m, int n, float* Q, int ldq, const float* W,
+                          int ldw);
+
+/* Explicit Q from a Householder WY pair.  Replaces later_ormqr (reference include/LATER.h:43,
+ * QR/later_ormqr.cu:18-64): W[:, n/2:] -= W[:, :n/2] * (Y[:, :n/2]^T W[:, n/2:]), then
+ * W <- I - W * Y[0:n, 0:n]^T.  fp32-faithful (split-precision tensor-core products). */
+int later_b200_ormqr(later_b200_ctx* ctx, int m, int n, float* W, int ldw, const float* Y,
+                     int ldy);
+/* Second step only (reference later_ormqr2, QR/later_ormqr.cu:66-85). */
+int later_b200_ormqr2(later_b200_ctx* ctx, int m, int n, float* W, int ldw, const float* Y,
+                      int ldy);
+
+/* ---- diagnostics: the two trailing-update GEMMs on their own (used by tests and profiles) ---- */
+/* C[Mc x Nc] = Qh(:, colA:colA+Mc)^T * Qh(:, colB:colB+Nc) over k_rows rows; Qh is device fp16
+ * column-major with leading dimension ldq (multiple of 8).  splits <= 0 picks automatically. */
+int later_b200_gemm_gram(later_b200_ctx* ctx, const void* Qh, int q_rows, int q_cols, long ldq,
+                         int colA, int Mc, int colB, int Nc, float* C, long ldc, void* Ch,
+                         long ldch, int splits);
+/* C[Mr x Nc] (-)= Qh(:, colA:colA+K) * Bh[K x Nc]  (Bh device fp16 column-major, ld ldb). */
+int later_b200_gemm_update(later_b200_ctx* ctx, const void* Qh, int q_rows, int q_cols, long ldq,
+                           int colA, int K, const void* Bh, long ldb, int Nc, float* C, long ldc,
+                           void* Ch, long ldch, int subtract);
+
+/* Number of kernels launched by the most recent call on this context (for bench.py). */
+long later_b200_last_launch_count(const later_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATER_B200_H */

@@ -1,0 +1,472 @@
+// Recursion driver for RGSQRF and the extern "C" entry points of include/later_b200.h.
+//
+// The recursion is the reference's (QR/later_rgsqrf.cu:25-60): split the columns in half, factor
+// the left half, R12 = Q1^T A2, A2 -= Q1 R12, factor the right half; 128-column base case.  What
+// differs is everything underneath:
+//   * operands of the two products are fp16 exactly as in the reference (RN cast of Q1, A2 and of
+//     R12), but the casts are fused into the producers: the panel kernel and the update kernel
+//     write an fp16 shadow of every column they finalise, the gram kernel emits fp16 R12 from its
+//     epilogue.  The reference's three s2h passes per node (util/util.cu:24-32) disappear; one
+//     initial cast of A remains.
+//   * the products are hand-written tcgen05 kernels (tc_gemm.cu), not cublasGemmEx.
+//   * the base case is one Gram/Cholesky panel (panel.cu), not the 26-launch CAQR chain.
+//   * the whole launch sequence (~1 000 launches for 16384^2) is captured once into a CUDA graph
+//     and replayed; the reference serialises ~4 000 launches on the legacy stream.
+#include "../../include/later_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "context.h"
+#include "panel.cuh"
+#include "tc_gemm.cuh"
+
+namespace lb {
+
+int fail(later_b200_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->error = msg;
+    return code;
+}
+int cuda_fail(later_b200_ctx* ctx, cudaError_t e, const char* where) {
+    if (ctx) ctx->error = std::string(where) + ": " + cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    return (int)e;
+}
+
+namespace {
+
+constexpr int NMIN = kPanelWidth;  // base-case width, reference QR/later_rgsqrf.cu:23
+
+inline long round_up(long x, long a) { return (x + a - 1) / a * a; }
+
+// fp32 -> fp16 (RN) of columns [c0, n) of A into the shadow; 8 elements per thread when aligned.
+__global__ void cast_shadow_kernel(const float* __restrict__ A, long lda, int m, int c0, int n,
+                                   __half* __restrict__ Qh, long ldh, int vec_ok) {
+    const int col = c0 + blockIdx.y;
+    if (col >= n) return;
+    const float* src = A + (long)col * lda;
+    __half* dst = Qh + (long)col * ldh;
+    if (vec_ok) {
+        for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8; i < m;
+             i += gridDim.x * blockDim.x * 8) {
+            const float4 a = *reinterpret_cast<const float4*>(src + i);
+            const float4 b = *reinterpret_cast<const float4*>(src + i + 4);
+            __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+            __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+            uint4 out;
+            out.x = *reinterpret_cast<uint32_t*>(&h0);
+            out.y = *reinterpret_cast<uint32_t*>(&h1);
+            out.z = *reinterpret_cast<uint32_t*>(&h2);
+            out.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(dst + i) = out;
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+            dst[i] = __float2half_rn(src[i]);
+    }
+}
+
+struct Workspace {
+    size_t qh_bytes, r12h_bytes, wh_bytes, part_bytes, panel_bytes, total;
+    long ldh;
+};
+
+int gram_bn(int h) { return h >= 256 ? 256 : 128; }
+
+Workspace plan_workspace(int num_sms, int m, int n) {
+    Workspace w{};
+    w.ldh = round_up(m, 8);
+    w.qh_bytes = (size_t)w.ldh * n * sizeof(__half);
+    w.r12h_bytes = n > NMIN ? (size_t)(n / 2) * (n / 2) * sizeof(__half) : 0;
+    size_t part = 0;
+    for (int h = NMIN; h * 2 <= n; h *= 2) {
+        const int s = choose_gram_splits(num_sms, h, h, gram_bn(h), m);
+        if (s > 1) part = std::max(part, (size_t)s * h * h * sizeof(float));
+    }
+    w.part_bytes = part;
+    w.panel_bytes = panel_scratch_bytes(m, num_sms);
+    w.wh_bytes = (size_t)n * n * sizeof(__half);  // fp16 W of the TSQR back-multiplication
+    w.total = round_up(w.qh_bytes, 256) + round_up(w.r12h_bytes, 256) + round_up(w.wh_bytes, 256) +
+              round_up(w.part_bytes, 256) + round_up(w.panel_bytes, 256) + 4096;
+    return w;
+}
+
+struct Recursion {
+    later_b200_ctx* ctx;
+    later_b200_ctx::Plan* p;
+    CUtensorMap q128, q256, q64;
+    cudaError_t err = cudaSuccess;
+    long launches = 0;
+
+    void check(cudaError_t e) {
+        if (err == cudaSuccess && e != cudaSuccess) err = e;
+    }
+
+    void qr(int c0, int w) {
+        if (err != cudaSuccess) return;
+        cudaStream_t st = ctx->stream;
+        if (w <= NMIN) {
+            check(panel_qr128(st, ctx->num_sms, p->m, p->A + (long)c0 * p->lda, p->lda,
+                              p->R + c0 + (long)c0 * p->ldr, p->ldr, p->Qh + (long)c0 * p->ldh,
+                              p->ldh, p->panel_scratch));
+            launches += 4;
+            return;
+        }
+        const int h = w / 2;
+        qr(c0, h);
+        if (err != cudaSuccess) return;
+        const int bn = gram_bn(h);
+        float* R12 = p->R + c0 + (long)(c0 + h) * p->ldr;
+        // R21 block is never produced by the algorithm: make it an explicit zero (the reference
+        // leaves it untouched and relies on a fresh cudaMalloc, test/test_qr.cu:49-50).
+        check(cudaMemset2DAsync(p->R + (c0 + h) + (long)c0 * p->ldr, (size_t)p->ldr * sizeof(float),
+                                0, (size_t)h * sizeof(float), h, st));
+        // R12 = Q1^T A2 (fp32 into R, fp16 copy for the update)
+        const int splits = choose_gram_splits(ctx->num_sms, h, h, bn, p->m);
+        check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, c0 + h, h,
+                      R12, p->ldr, p->R12h, h, p->part, splits));
+        launches += splits > 1 ? 2 : 1;
+        // A2 -= Q1 R12, refreshing A2's fp16 shadow
+        CUtensorMap r12map;
+        HalfMatrix rm{p->R12h, h, h, h};
+        check(make_tensor_map_f16(&r12map, rm, 64, bn));
+        check(tc_update(st, ctx->num_sms, q64, r12map, bn, 0, p->m, c0, h, 0, h,
+                        p->A + (long)(c0 + h) * p->lda, p->lda, p->Qh + (long)(c0 + h) * p->ldh,
+                        p->ldh, true));
+        launches += 1;
+        qr(c0 + h, h);
+    }
+};
+
+int validate(later_b200_ctx* ctx, int m, int n, const void* A, int lda, const void* R, int ldr) {
+    if (!ctx) return LATER_B200_EINVAL;
+    if (!A || !R) return fail(ctx, LATER_B200_EINVAL, "null matrix pointer");
+    if (n <= 0 || n % NMIN != 0)
+        return fail(ctx, LATER_B200_EINVAL, "n must be a positive multiple of 128");
+    if (m < n) return fail(ctx, LATER_B200_EINVAL, "m must be >= n");
+    if (m % 8 != 0) return fail(ctx, LATER_B200_EINVAL, "m must be a multiple of 8");
+    if (lda < m || ldr < n) return fail(ctx, LATER_B200_EINVAL, "leading dimension too small");
+    if ((long)m * n > (long)1 << 34) return fail(ctx, LATER_B200_EINVAL, "matrix too large");
+    return 0;
+}
+
+// Reserves and carves the workspace for (m, n); fills ctx->plan.
+int prepare_plan(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
+    const Workspace w = plan_workspace(ctx->num_sms, m, n);
+    cudaError_t e = ctx->arena.reserve(w.total);
+    if (e != cudaSuccess) {
+        cuda_fail(ctx, e, "workspace reserve");
+        return LATER_B200_ENOMEM;
+    }
+    ctx->arena.reset();
+    auto& p = ctx->plan;
+    p.m = m; p.n = n; p.A = A; p.lda = lda; p.R = R; p.ldr = ldr;
+    p.ldh = w.ldh;
+    p.Qh = static_cast<__half*>(ctx->arena.alloc(w.qh_bytes));
+    p.R12h = w.r12h_bytes ? static_cast<__half*>(ctx->arena.alloc(w.r12h_bytes)) : nullptr;
+    p.Wh = static_cast<__half*>(ctx->arena.alloc(w.wh_bytes));
+    p.part = w.part_bytes ? static_cast<float*>(ctx->arena.alloc(w.part_bytes)) : nullptr;
+    p.part_floats = w.part_bytes / sizeof(float);
+    p.panel_scratch = ctx->arena.alloc(w.panel_bytes);
+    p.arena_gen = ctx->arena.generation();
+    p.valid = p.Qh && p.Wh && p.panel_scratch && (!w.r12h_bytes || p.R12h) && (!w.part_bytes || p.part);
+    if (!p.valid) return fail(ctx, LATER_B200_ENOMEM, "workspace carve failed");
+    return 0;
+}
+
+// Enqueues the whole factorisation on ctx->stream (directly, or into an ongoing capture).
+int enqueue_factorisation(later_b200_ctx* ctx, long* launches) {
+    auto& p = ctx->plan;
+    Recursion rec{};
+    rec.ctx = ctx;
+    rec.p = &p;
+    HalfMatrix qm{p.Qh, p.m, p.n, p.ldh};
+    cudaError_t e;
+    if ((e = make_tensor_map_f16(&rec.q128, qm, 64, 128)) != cudaSuccess ||
+        (e = make_tensor_map_f16(&rec.q256, qm, 64, 256)) != cudaSuccess ||
+        (e = make_tensor_map_f16(&rec.q64, qm, 64, 64)) != cudaSuccess)
+        return cuda_fail(ctx, e, "tensor map encode");
+    if (p.n > NMIN) {
+        const int vec_ok = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+        dim3 grid((unsigned)std::min<long>((p.m / 8 + 255) / 256, 64), (unsigned)(p.n - NMIN));
+        cast_shadow_kernel<<<grid, 256, 0, ctx->stream>>>(p.A, p.lda, p.m, NMIN, p.n, p.Qh, p.ldh,
+                                                          vec_ok);
+        rec.launches += 1;
+    }
+    rec.qr(0, p.n);
+    if (rec.err != cudaSuccess) return cuda_fail(ctx, rec.err, "rgsqrf enqueue");
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "rgsqrf launch");
+    *launches = rec.launches;
+    return 0;
+}
+
+bool same_plan(const later_b200_ctx::Plan& a, const later_b200_ctx::Plan& b) {
+    return a.valid && b.valid && a.m == b.m && a.n == b.n && a.A == b.A && a.lda == b.lda &&
+           a.R == b.R && a.ldr == b.ldr && a.Qh == b.Qh && a.arena_gen == b.arena_gen;
+}
+
+int rgsqrf_device(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
+    int rc = validate(ctx, m, n, A, lda, R, ldr);
+    if (rc) return rc;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    rc = prepare_plan(ctx, m, n, A, lda, R, ldr);
+    if (rc) return rc;
+
+    if (!ctx->use_graph) {
+        return enqueue_factorisation(ctx, &ctx->launches);
+    }
+    if (ctx->graph_exec && same_plan(ctx->graph_plan, ctx->plan)) {
+        e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
+        ctx->launches = ctx->graph_launches;
+        return 0;
+    }
+    if (ctx->graph_exec) {
+        cudaGraphExecDestroy(ctx->graph_exec);
+        ctx->graph_exec = nullptr;
+    }
+    // Capture on a private stream so the legacy default stream can be the context's stream.
+    cudaStream_t cap = nullptr;
+    if ((e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking)) != cudaSuccess)
+        return cuda_fail(ctx, e, "capture stream");
+    cudaStream_t user = ctx->stream;
+    ctx->stream = cap;
+    long launches = 0;
+    e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { ctx->stream = user; cudaStreamDestroy(cap); return cuda_fail(ctx, e, "begin capture"); }
+    rc = enqueue_factorisation(ctx, &launches);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(cap, &graph);
+    ctx->stream = user;
+    cudaStreamDestroy(cap);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "end capture");
+    e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { ctx->graph_exec = nullptr; return cuda_fail(ctx, e, "graph instantiate"); }
+    ctx->graph_plan = ctx->plan;
+    ctx->graph_launches = launches;
+    ctx->launches = launches;
+    e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
+    return 0;
+}
+
+__global__ void cast_matrix_kernel(const float* __restrict__ S, long lds, int rows, int cols,
+                                   __half* __restrict__ D, long ldd) {
+    const long total = (long)rows * cols;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % rows), j = (int)(idx / rows);
+        D[i + (long)j * ldd] = __float2half_rn(S[i + (long)j * lds]);
+    }
+}
+
+}  // namespace
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" {
+
+int later_b200_create(later_b200_ctx** out, int device, void* stream) {
+    if (!out) return LATER_B200_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        (void)cudaGetLastError();
+        return LATER_B200_ENODEV;
+    }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LATER_B200_ENODEV;
+    if (prop.major != 10) return LATER_B200_ENODEV;  // tcgen05 kernels: sm_100a only, no fallback
+    if (cudaSetDevice(device) != cudaSuccess) return LATER_B200_ENODEV;
+    later_b200_ctx* ctx = new (std::nothrow) later_b200_ctx();
+    if (!ctx) return LATER_B200_ENOMEM;
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    ctx->arena.bind(ctx->stream);
+    // keep freed workspace cached in the default pool instead of returning it to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thresh = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    cudaError_t e = tc_gemm_init();
+    if (e == cudaSuccess) e = panel_init();
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(ctx, e, "kernel attribute setup");
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return 0;
+}
+
+int later_b200_destroy(later_b200_ctx* ctx) {
+    if (!ctx) return LATER_B200_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->dA) cudaFree(ctx->dA);
+    if (ctx->dR) cudaFree(ctx->dR);
+    ctx->arena.release();
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+const char* later_b200_last_error(const later_b200_ctx* ctx) {
+    return ctx ? ctx->error.c_str() : "null context";
+}
+
+int later_b200_set_graph(later_b200_ctx* ctx, int enable) {
+    if (!ctx) return LATER_B200_EINVAL;
+    ctx->use_graph = enable != 0;
+    return 0;
+}
+
+size_t later_b200_workspace_bytes(const later_b200_ctx* ctx, int m, int n) {
+    if (!ctx || n <= 0 || m < n) return 0;
+    return plan_workspace(ctx->num_sms, m, n).total;
+}
+
+long later_b200_last_launch_count(const later_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
+    return rgsqrf_device(ctx, m, n, A, lda, R, ldr);
+}
+
+int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda, float* hR,
+                           int ldr) {
+    int rc = validate(ctx, m, n, hA, lda, hR, ldr);
+    if (rc) return rc;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    const size_t a_bytes = (size_t)m * n * sizeof(float), r_bytes = (size_t)n * n * sizeof(float);
+    if (ctx->dA_bytes < a_bytes) {
+        if (ctx->dA) cudaFree(ctx->dA);
+        ctx->dA = nullptr; ctx->dA_bytes = 0;
+        if ((e = cudaMalloc(&ctx->dA, a_bytes)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc A");
+        ctx->dA_bytes = a_bytes;
+    }
+    if (ctx->dR_bytes < r_bytes) {
+        if (ctx->dR) cudaFree(ctx->dR);
+        ctx->dR = nullptr; ctx->dR_bytes = 0;
+        if ((e = cudaMalloc(&ctx->dR, r_bytes)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc R");
+        ctx->dR_bytes = r_bytes;
+    }
+    e = cudaMemcpy2DAsync(ctx->dA, (size_t)m * sizeof(float), hA, (size_t)lda * sizeof(float),
+                          (size_t)m * sizeof(float), n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "H2D A");
+    rc = rgsqrf_device(ctx, m, n, ctx->dA, m, ctx->dR, n);
+    if (rc) return rc;
+    e = cudaMemcpy2DAsync(hA, (size_t)lda * sizeof(float), ctx->dA, (size_t)m * sizeof(float),
+                          (size_t)m * sizeof(float), n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(hR, (size_t)ldr * sizeof(float), ctx->dR, (size_t)n * sizeof(float),
+                              (size_t)n * sizeof(float), n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "D2H Q/R");
+    return 0;
+}
+
+int later_b200_panel_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
+    if (!ctx) return LATER_B200_EINVAL;
+    if (n != kPanelWidth) return fail(ctx, LATER_B200_EINVAL, "panel width must be 128");
+    if (!A || !R || m < n || lda < m || ldr < n) return fail(ctx, LATER_B200_EINVAL, "bad panel arguments");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    const size_t bytes = panel_scratch_bytes(m, ctx->num_sms);
+    if ((e = ctx->arena.reserve(bytes + 4096)) != cudaSuccess) {
+        cuda_fail(ctx, e, "workspace reserve");
+        return LATER_B200_ENOMEM;
+    }
+    ctx->arena.reset();
+    ctx->plan.valid = false;
+    void* scratch = ctx->arena.alloc(bytes);
+    e = panel_qr128(ctx->stream, ctx->num_sms, m, A, lda, R, ldr, nullptr, 0, scratch);
+    ctx->launches = 4;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "panel_qr128");
+    return 0;
+}
+
+int later_b200_tsqr_apply(later_b200_ctx* ctx, int m, int n, float* Q, int ldq, const float* W,
+                          int ldw) {
+    if (!ctx) return LATER_B200_EINVAL;
+    auto& p = ctx->plan;
+    if (!p.valid || p.m != m || p.n != n || p.A != Q || p.lda != ldq)
+        return fail(ctx, LATER_B200_ESTATE, "tsqr_apply needs the preceding rgsqrf on the same Q");
+    if (!W || ldw < n) return fail(ctx, LATER_B200_EINVAL, "bad W");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    cast_matrix_kernel<<<std::min(1184, (n * n + 255) / 256), 256, 0, ctx->stream>>>(W, ldw, n, n,
+                                                                                     p.Wh, n);
+    CUtensorMap q64, wmap;
+    HalfMatrix qm{p.Qh, p.m, p.n, p.ldh}, wm{p.Wh, n, n, n};
+    const int bn = n >= 256 ? 256 : 128;
+    if ((e = make_tensor_map_f16(&q64, qm, 64, 64)) == cudaSuccess &&
+        (e = make_tensor_map_f16(&wmap, wm, 64, bn)) == cudaSuccess)
+        e = tc_update(ctx->stream, ctx->num_sms, q64, wmap, bn, 0, m, 0, n, 0, n, Q, ldq, nullptr,
+                      0, false);
+    ctx->launches = 2;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "tsqr_apply");
+    return 0;
+}
+
+int later_b200_gemm_gram(later_b200_ctx* ctx, const void* Qh, int q_rows, int q_cols, long ldq,
+                         int colA, int Mc, int colB, int Nc, float* C, long ldc, void* Ch,
+                         long ldch, int splits) {
+    if (!ctx || !Qh || !C) return LATER_B200_EINVAL;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    const int bn = Nc >= 256 ? 256 : 128;
+    if (splits <= 0) splits = choose_gram_splits(ctx->num_sms, Mc, Nc, bn, q_rows);
+    float* part = nullptr;
+    if (splits > 1) {
+        if ((e = ctx->arena.reserve((size_t)splits * Mc * Nc * sizeof(float) + 4096)) != cudaSuccess) {
+            cuda_fail(ctx, e, "workspace reserve");
+            return LATER_B200_ENOMEM;
+        }
+        ctx->arena.reset();
+        ctx->plan.valid = false;
+        part = static_cast<float*>(ctx->arena.alloc((size_t)splits * Mc * Nc * sizeof(float)));
+    }
+    CUtensorMap q128, qbn;
+    HalfMatrix qm{static_cast<const __half*>(Qh), q_rows, q_cols, ldq};
+    if ((e = make_tensor_map_f16(&q128, qm, 64, 128)) != cudaSuccess ||
+        (e = make_tensor_map_f16(&qbn, qm, 64, bn)) != cudaSuccess)
+        return cuda_fail(ctx, e, "tensor map encode");
+    e = tc_gram(ctx->stream, ctx->num_sms, q128, qbn, bn, 0, q_rows, colA, Mc, colB, Nc, C, ldc,
+                static_cast<__half*>(Ch), ldch, part, splits);
+    ctx->launches = splits > 1 ? 2 : 1;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "tc_gram");
+    return 0;
+}
+
+int later_b200_gemm_update(later_b200_ctx* ctx, const void* Qh, int q_rows, int q_cols, long ldq,
+                           int colA, int K, const void* Bh, long ldb, int Nc, float* C, long ldc,
+                           void* Ch, long ldch, int subtract) {
+    if (!ctx || !Qh || !Bh || !C) return LATER_B200_EINVAL;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    const int bn = Nc >= 256 ? 256 : 128;
+    CUtensorMap q64, bmap;
+    HalfMatrix qm{static_cast<const __half*>(Qh), q_rows, q_cols, ldq};
+    HalfMatrix bm{static_cast<const __half*>(Bh), K, Nc, ldb};
+    if ((e = make_tensor_map_f16(&q64, qm, 64, 64)) != cudaSuccess ||
+        (e = make_tensor_map_f16(&bmap, bm, 64, bn)) != cudaSuccess)
+        return cuda_fail(ctx, e, "tensor map encode");
+    e = tc_update(ctx->stream, ctx->num_sms, q64, bmap, bn, 0, q_rows, colA, K, 0, Nc, C, ldc,
+                  static_cast<__half*>(Ch), ldch, subtract != 0);
+    ctx->launches = 1;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "tc_update");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// Host-side interface of the tcgen05 GEMM kernels that carry RGSQRF's trailing updates.
+//
+// They replace the two cublasGemmEx calls plus the three separate s2h cast kernels of the
+// reference recursion (reference QR/later_rgsqrf.cu:41-56):
+//   gram   : R12 = Q1^T * A2      (both operands K-major: K runs down the rows of the column-major
+//                                   fp16 shadow, so it is the contiguous dimension)
+//   update : A2 -= Q1 * R12       (A operand MN-major, B operand K-major, fp32 read-modify-write)
+//   assign : C   = Qh * W         (same operand layout as update, no C read; TSQR back-multiply)
+// Operands are fp16 ("shadow" copies written by the producing kernels' epilogues), accumulation is
+// fp32 in TMEM, exactly the arithmetic cublasGemmEx(CUDA_R_16F in, CUDA_R_32F compute) performs.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace lb {
+
+// A 2-D fp16 matrix in device memory, column-major, as the TMA unit sees it.
+struct HalfMatrix {
+    const __half* ptr;  // element (0,0)
+    int rows;           // extent of the contiguous dimension
+    int cols;
+    long ld;            // leading dimension in elements (multiple of 8 -> 16-byte strides)
+};
+
+enum EpiMode : int {
+    EPI_STORE = 0,    // C = D            (+ optional fp16 copy)
+    EPI_SUB = 1,      // C = C - D        (+ optional fp16 copy of the new C)
+    EPI_PARTIAL = 2,  // part[split] = D  (split-K; reduced by splitk_reduce)
+    EPI_ADD = 3,      // C = C + D
+};
+
+struct TcGemmParams {
+    int M, N;               // output extent
+    int kb_total;           // 64-wide k blocks over the whole K
+    int kb_per_split;
+    int splits;
+    int tiles_m, tiles_n;
+    int a_c0, a_c1;         // TMA origin of the A operand (inner, outer)
+    int b_c0, b_c1;         // TMA origin of the B operand (inner = K, outer = N)
+    float* C;
+    long ldc;
+    __half* Ch;             // optional fp16 mirror of C
+    long ldch;
+    float* part;            // split-K workspace: [splits][N][M]
+    const float* dscale;    // optional device scalar multiplied into D before the epilogue op
+};
+
+// Encodes a SWIZZLE_128B tiled tensor map over a column-major fp16 matrix with box
+// {box_inner (<=64), box_outer (<=256)}.  Returns cudaSuccess or the failure.
+cudaError_t make_tensor_map_f16(CUtensorMap* out, const HalfMatrix& mat, int box_inner,
+                                int box_outer);
+
+struct TcGemmPlan {
+    int bn;        // 128 or 256
+    int splits;
+    int kb_per_split;
+    int grid;
+};
+
+// R12[Mc x Nc] (fp32, ld ldc) = A1^T * A2 with A1 = Q(:, colA : colA+Mc), A2 = Q(:, colB : colB+Nc),
+// K = rows [row0, row0 + k_rows) of the fp16 shadow Q.  Optional fp16 copy of R12 into Ch.
+// `part` must hold splits*Mc*Nc floats when the plan uses split-K.
+cudaError_t tc_gram(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128,
+                    const CUtensorMap& mapQ_bn, int bn, int row0, int k_rows, int colA, int Mc,
+                    int colB, int Nc, float* C, long ldc, __half* Ch, long ldch, float* part,
+                    int splits);
+
+// C[Mr x Nc] (fp32, ld ldc) (-)= Qh(row0:row0+Mr, colA:colA+K) * Bh[K x Nc]; Bh is addressed through
+// its own tensor map with origin (0, colB0).  sub=true: C -= D; sub=false: C = D.  Optional fp16
+// mirror of the new C into Ch.
+cudaError_t tc_update(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_64,
+                      const CUtensorMap& mapB_bn, int bn, int row0, int Mr, int colA, int K,
+                      int colB0, int Nc, float* C, long ldc, __half* Ch, long ldch, bool sub);
+
+// Generic launch: a_mn_major=false -> both operands K-major ("gram" layout, modes STORE / PARTIAL /
+// ADD); a_mn_major=true -> A MN-major ("update" layout, modes SUB / STORE).
+cudaError_t tc_gemm_launch(cudaStream_t stream, int num_sms, bool a_mn_major, int bn, int epi,
+                           const CUtensorMap& mapA, const CUtensorMap& mapB, const TcGemmParams& p);
+void tc_fill_gram(TcGemmParams& p, int bn, int row0, int k_rows, int colA, int Mc, int colB, int Nc,
+                  float* C, long ldc, __half* Ch, long ldch);
+void tc_fill_update(TcGemmParams& p, int bn, int row0, int Mr, int colA, int K, int colB0, int Nc,
+                    float* C, long ldc, __half* Ch, long ldch);
+
+// Sums split-K partials in a fixed order (deterministic) and writes C (+ fp16 copy).
+cudaError_t splitk_reduce(cudaStream_t stream, const float* part, int splits, int M, int N, float* C,
+                          long ldc, __half* Ch, long ldch);
+
+// Picks split-K so that tiles*splits roughly fills the machine.
+int choose_gram_splits(int num_sms, int Mc, int Nc, int bn, int k_rows);
+
+// Sets the dynamic shared-memory limits of all kernel instantiations (once per device).
+cudaError_t tc_gemm_init();
+
+}  // namespace lb
