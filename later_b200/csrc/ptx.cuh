@@ -33,17 +33,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Spin until the phase with the given parity has completed.  With LB_SPIN_LIMIT defined the
-// wait traps after that many polls, so a protocol bug shows up as a launch failure, not a hang.
+// Spin until the phase with the given parity has completed.  The wait traps after LB_SPIN_LIMIT
+// polls (tens of seconds), so a protocol bug shows up as a launch failure, not a hung GPU.
+#ifndef LB_SPIN_LIMIT
+#define LB_SPIN_LIMIT (1ull << 28)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-#ifdef LB_SPIN_LIMIT
     unsigned long long n = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++n > (unsigned long long)(LB_SPIN_LIMIT)) { __trap(); }
     }
-#else
-    while (!mbar_try_wait(bar, parity)) {}
-#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");

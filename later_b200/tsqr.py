@@ -1,0 +1,78 @@
+"""Row-sharded tall-skinny QR over several GPUs (one process per GPU, torch.distributed).
+
+The reference has no multi-GPU code; the structure is the one its CAQR panel already uses inside
+one GPU across 256-row blocks (reference QR/panel.cu:87-104), lifted to ranks:
+
+  1. every rank factors its own row block   A_p = Q_p R_p          (later_rgsqrf, local)
+  2. the P small R_p (n x n) are exchanged                          (one all-gather: P * 4n^2 bytes)
+  3. every rank factors the same stack [R_0; ...; R_{P-1}] = W R    (redundantly; identical bits
+     on every rank because inputs and code are identical, so no broadcast of R or W is needed)
+  4. Q_p <- Q_p W_p                                                 (tensor-core GEMM, local)
+
+Only step 2 communicates.  `local_qr`, `stack_qr` and `apply_w` are injection points so that the
+host-side logic can be exercised on CPU (gloo) with the numpy oracle standing in for the kernels.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+
+def stack_from_gathered(gathered_t: torch.Tensor) -> torch.Tensor:
+    """gathered_t[p] holds R_p^T row-major (= R_p column-major), shape (P, n, n).  Returns the
+    column-major (P*n) x n stack [R_0; R_1; ...] as a tensor of shape (P*n, n), strides (1, P*n)."""
+    P, n, _ = gathered_t.shape
+    st = gathered_t.permute(1, 0, 2).reshape(n, P * n).contiguous()   # st[j, p*n + i] = R_p[i, j]
+    return st.t()
+
+
+def tsqr_rgsqrf(m_local: int, n: int, A: torch.Tensor, lda: int, R: torch.Tensor, ldr: int,
+                group=None,
+                local_qr: Callable | None = None,
+                stack_qr: Callable | None = None,
+                apply_w: Callable | None = None,
+                ctxs=None) -> None:
+    """In place: A (this rank's m_local x n row block, column-major) <- its block of the global Q;
+    R (n x n) <- the global R factor (identical on every rank)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    if local_qr is None:
+        from . import qr as _qr
+        if ctxs is None:
+            ctxs = (_qr.Context(), _qr.Context())
+        main_ctx, stack_ctx = ctxs
+
+        def local_qr(m, n_, a, lda_, r, ldr_):
+            _qr.later_rgsqrf(main_ctx, m, n_, a, lda_, r, ldr_)
+
+        def stack_qr(m, n_, s, lds, r, ldr_):
+            _qr.later_rgsqrf(stack_ctx, m, n_, s, lds, r, ldr_)
+
+        def apply_w(m, n_, q, ldq, w, ldw):
+            _qr.tsqr_apply(main_ctx, m, n_, q, ldq, w, ldw)
+
+    if world == 1:
+        local_qr(m_local, n, A, lda, R, ldr)
+        return
+
+    # 1. local factorisation into a contiguous n x n R_p
+    Rp = torch.empty((n, n), device=A.device, dtype=A.dtype).t()        # column-major, ld = n
+    local_qr(m_local, n, A, lda, Rp, n)
+
+    # 2. exchange: all-gather the column-major storage of every R_p
+    gathered = torch.empty((world * n, n), device=A.device, dtype=A.dtype)
+    dist.all_gather_into_tensor(gathered, Rp.t().contiguous(), group=group)
+    gathered = gathered.view(world, n, n)
+
+    # 3. redundant QR of the stack (canonical order: rank 0 on top)
+    S = stack_from_gathered(gathered)                                    # (P*n) x n, ld = P*n
+    Rs = torch.empty((n, n), device=A.device, dtype=A.dtype).t()
+    stack_qr(world * n, n, S, world * n, Rs, n)
+
+    # 4. back-multiplication with this rank's n x n block of the stack's Q
+    W = S[rank * n:(rank + 1) * n, :]                                    # column-major view, ld = P*n
+    apply_w(m_local, n, A, lda, W, world * n)
+    R[:n, :n].copy_(Rs)

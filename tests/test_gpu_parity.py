@@ -1,0 +1,336 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle on identical seeded
+inputs, against the committed outputs of the reference itself, and - at BASELINE.json's full sizes,
+where the oracle would take too long - through size-independent properties of a QR factorisation.
+
+Tolerances (floating point, so not bit-exact; BASELINE.json's bar):
+  * backward error ||A-QR||/||A|| and orthogonality ||I-Q^T Q||/n each within 2x of the
+    reference's (oracle or golden) value on the same input;
+  * fp16-tensor-core tolerance vs LAPACK: backward error <= 1e-3 (~2 u_fp16).
+"""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from oracle import rgsqrf_oracle as orc  # noqa: E402
+from tests.golden.make_golden import CASES, make_input  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="module")
+def qr():
+    from later_b200 import qr as _qr
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _qr
+
+
+@pytest.fixture(scope="module")
+def ctx(qr):
+    c = qr.Context()
+    yield c
+    c.close()
+
+
+def dev_colmajor(qr, a: np.ndarray) -> torch.Tensor:
+    t = qr.colmajor_empty(a.shape[0], a.shape[1])
+    t.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)))
+    return t
+
+
+def run_rgsqrf(qr, ctx, A0: np.ndarray):
+    m, n = A0.shape
+    A = dev_colmajor(qr, A0)
+    R = qr.colmajor_empty(n, n)
+    R.fill_(float("nan"))                     # every entry of R must be written by the library
+    qr.later_rgsqrf(ctx, m, n, A, m, R, n)
+    torch.cuda.synchronize()
+    return A.cpu().numpy(), R.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------ GEMM kernels
+@pytest.mark.parametrize("m,Mc,Nc,splits", [(1024, 128, 128, 1), (1024, 256, 256, 1),
+                                            (4096, 128, 128, 8), (8200, 512, 512, 0),
+                                            (2048, 1024, 1024, 1), (65536, 128, 128, 0)])
+def test_gram_kernel_vs_fp32_reference(qr, ctx, m, Mc, Nc, splits):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    Q = qr.to_colmajor(torch.randn(m, Mc + Nc, device="cuda", generator=g).half())
+    C = qr.colmajor_empty(Mc, Nc)
+    Ch = qr.colmajor_empty(Mc, Nc, dtype=torch.float16)
+    C.fill_(float("nan"))
+    qr.gemm_gram(ctx, Q, 0, Mc, Mc, Nc, C, Ch, splits)
+    ref = Q[:, :Mc].float().t() @ Q[:, Mc:].float()          # plain fp32 reference, same fp16 inputs
+    scale = ref.abs().max().item()
+    assert (C - ref).abs().max().item() <= 2e-5 * scale      # fp32 accumulation-order noise only
+    assert torch.equal(Ch, C.half())                          # fp16 copy is the RN cast of the result
+
+
+@pytest.mark.parametrize("m,K,Nc,sub", [(1024, 128, 128, True), (1000, 256, 256, True),
+                                        (4096, 512, 512, True), (2048, 256, 256, False),
+                                        (16384, 1024, 128, True)])
+def test_update_kernel_vs_fp32_reference(qr, ctx, m, K, Nc, sub):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    Q = qr.to_colmajor(torch.randn(m, K + 64, device="cuda", generator=g).half())
+    B = qr.to_colmajor((torch.randn(K, Nc, device="cuda", generator=g) / 8).half())
+    C0 = qr.to_colmajor(torch.randn(m, Nc, device="cuda", generator=g))
+    C = qr.to_colmajor(C0.clone())
+    Ch = qr.colmajor_empty(m, Nc, dtype=torch.float16)
+    qr.gemm_update(ctx, Q, 64, K, B, C, Ch, sub)
+    prod = Q[:, 64:64 + K].float() @ B.float()
+    ref = C0 - prod if sub else prod
+    assert (C - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert torch.equal(Ch, C.half())
+
+
+# ------------------------------------------------------------------------------ panel
+@pytest.mark.parametrize("m,dist", [(128, "normal"), (256, "uniform"), (320, "normal"),
+                                    (1024, "uniform"), (5000, "normal"), (65536, "uniform")])
+def test_panel_vs_oracle(qr, ctx, m, dist):
+    rng = np.random.default_rng(m)
+    A0 = rng.random((m, 128), dtype=np.float32) if dist == "uniform" else rng.standard_normal((m, 128), dtype=np.float32)
+    A = dev_colmajor(qr, A0)
+    R = qr.colmajor_empty(128, 128)
+    R.fill_(float("nan"))
+    qr.mgs_caqr_panel_256x128(ctx, m, 128, A, m, R, 128)
+    Q, R = A.cpu().numpy(), R.cpu().numpy()
+    assert np.abs(np.tril(R, -1)).max() == 0.0 and (np.diag(R) > 0).all()
+    Qo = np.array(A0, order="F", copy=True)
+    Ro = np.zeros((128, 128), dtype=np.float32)
+    orc.mgs_caqr_panel_256x128(Qo, Ro)
+    # same fp32-level quality as the reference's MGS/CAQR panel ...
+    assert orc.check_result(A0, Q, R) <= max(2 * orc.check_result(A0, Qo, Ro), 5e-7)
+    assert orc.check_otho(Q) <= max(2 * orc.check_otho(Qo), 5e-8)
+    # ... and the same factors (QR with r_ii > 0 is unique), up to fp32 rounding times conditioning
+    cond = np.linalg.cond(A0.astype(np.float64))
+    assert np.abs(R - Ro).max() <= 1e-5 * cond * np.abs(Ro).max()
+    assert np.abs(Q - Qo).max() <= 1e-5 * cond
+
+
+# ------------------------------------------------------------------------------ RGSQRF vs oracle
+@pytest.mark.parametrize("m,n,dist", [(256, 256, "normal"), (512, 256, "normal"), (1024, 512, "uniform"),
+                                      (1024, 1024, "uniform"), (2048, 1024, "normal"), (800, 128, "normal")])
+def test_rgsqrf_vs_oracle(qr, ctx, m, n, dist):
+    rng = np.random.default_rng(1000 + m + n)
+    A0 = rng.random((m, n), dtype=np.float32) if dist == "uniform" else rng.standard_normal((m, n), dtype=np.float32)
+    Q, R = run_rgsqrf(qr, ctx, A0)
+    Qo, Ro = orc.later_rgsqrf(A0)
+    assert np.isfinite(R).all() and np.abs(np.tril(R, -1)).max() == 0.0 and (np.diag(R) > 0).all()
+    back, orth = orc.check_result(A0, Q, R), orc.check_otho(Q)
+    back_o, orth_o = orc.check_result(A0, Qo, Ro), orc.check_otho(Qo)
+    assert back <= 2 * back_o + 1e-7, (back, back_o)
+    assert orth <= 2 * orth_o + 1e-7, (orth, orth_o)
+    assert back <= 1e-3                                       # fp16-TC tolerance vs LAPACK (~5e-7)
+    cond = np.linalg.cond(A0.astype(np.float64))
+    assert np.abs(R - Ro).max() <= 2e-3 * cond * np.abs(Ro).max()
+
+
+@pytest.mark.parametrize("name", [k for k, v in CASES.items() if v[0] == "rgsqrf"])
+def test_rgsqrf_vs_reference_golden(qr, ctx, name):
+    kind, m, n, dist, seed = CASES[name]
+    g = np.load(GOLD / f"{name}.npz")
+    A0 = make_input(kind, m, n, dist, seed)
+    Q, R = run_rgsqrf(qr, ctx, A0)
+    assert orc.check_result(A0, Q, R) <= 2 * float(g["backward"])
+    assert orc.check_otho(Q) <= 2 * float(g["orth"])
+    assert np.abs(np.triu(R) - np.triu(g["R"])).max() <= 2e-3 * np.abs(g["R"]).max()
+    assert np.abs(Q[::8, :] - g["Q_rows8"]).max() <= 2e-3
+
+
+@pytest.mark.parametrize("name", [k for k, v in CASES.items() if v[0] == "panel"])
+def test_panel_vs_reference_golden(qr, ctx, name):
+    kind, m, n, dist, seed = CASES[name]
+    g = np.load(GOLD / f"{name}.npz")
+    A0 = make_input(kind, m, n, dist, seed)
+    A = dev_colmajor(qr, A0)
+    R = qr.colmajor_empty(128, 128)
+    qr.mgs_caqr_panel_256x128(ctx, m, 128, A, m, R, 128)
+    Q, R = A.cpu().numpy(), R.cpu().numpy()
+    assert orc.check_result(A0, Q, R) <= max(2 * float(g["backward"]), 5e-7)
+    assert orc.check_otho(Q) <= max(2 * float(g["orth"]), 5e-8)
+    assert np.abs(np.triu(R) - np.triu(g["R"])).max() <= 2e-5 * np.abs(g["R"]).max()
+    assert np.abs(Q[::8, :] - g["Q_rows8"]).max() <= 2e-5
+
+
+# ------------------------------------------------------------------------------ full-size properties
+def _factor_device(qr, ctx, A0: torch.Tensor):
+    m, n = A0.shape
+    A = qr.to_colmajor(A0)
+    R = qr.colmajor_empty(n, n)
+    R.fill_(float("nan"))
+    qr.later_rgsqrf(ctx, m, n, A, m, R, n)
+    return A, R
+
+
+@pytest.mark.parametrize("m,n,dist,back_max,orth_max", [
+    (16384, 16384, "uniform", 5.1e-4, 7.9e-4),   # config 2; reference on its own input: 2.52e-4 / 3.90e-4
+    (262144, 256, "normal", 1e-4, 1e-5),         # config 3
+    (131072, 1024, "normal", 2e-4, 2e-5),        # one 8-GPU shard of config 4
+])
+def test_full_size_properties(qr, ctx, m, n, dist, back_max, orth_max):
+    g = torch.Generator(device="cuda").manual_seed(3000)
+    A0 = (torch.rand if dist == "uniform" else torch.randn)(m, n, device="cuda", generator=g)
+    Q, R = _factor_device(qr, ctx, A0)
+    assert torch.isfinite(R).all()
+    assert torch.tril(R, -1).abs().max().item() == 0.0          # R upper triangular, explicitly
+    assert (R.diagonal() > 0).all()
+    assert qr.backward_error(A0, Q, R) <= back_max              # A = Q R
+    assert qr.orthogonality(Q) <= orth_max                      # Q^T Q = I
+    # column norms: |r_jj| <= ||a_j||, and ||R||_F = ||A||_F up to the orthogonality defect
+    assert abs(float(torch.linalg.norm(R.double()) / torch.linalg.norm(A0.double())) - 1.0) <= 1e-2
+
+
+def test_scaling_by_powers_of_two_is_exact(qr, ctx):
+    """Linearity: QR(4 A) = Q (4 R) bit for bit - every operation commutes with power-of-two scaling."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A0 = torch.randn(2048, 512, device="cuda", generator=g)
+    Q1, R1 = _factor_device(qr, ctx, A0)
+    Q2, R2 = _factor_device(qr, ctx, A0 * 4.0)
+    assert torch.equal(Q1, Q2) and torch.equal(R1 * 4.0, R2)
+
+
+def test_requantising_q_is_idempotent(qr, ctx):
+    """QR of an (almost) orthonormal Q returns R ~ I and Q back."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    Q, _ = _factor_device(qr, ctx, torch.randn(4096, 512, device="cuda", generator=g))
+    Q2, R2 = _factor_device(qr, ctx, Q.clone())
+    eye = torch.eye(512, device="cuda")
+    assert (R2 - eye).abs().max().item() <= 2e-3
+    assert (Q2 - Q).abs().max().item() <= 2e-3
+
+
+def test_deterministic_and_graph_equals_stream(qr):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    A0 = torch.rand(4096, 1024, device="cuda", generator=g)
+    outs = []
+    for use_graph in (True, True, False):
+        c = qr.Context(use_graph=use_graph)
+        for _ in range(2):                       # second call replays the cached graph
+            Q, R = _factor_device(qr, c, A0)
+        A2 = qr.to_colmajor(A0)
+        R2 = qr.colmajor_empty(1024, 1024)
+        qr.later_rgsqrf(c, 4096, 1024, A2, 4096, R2, 1024)
+        outs.append((A2.clone(), R2.clone()))
+        c.close()
+    for Q, R in outs[1:]:
+        assert torch.equal(Q, outs[0][0]) and torch.equal(R, outs[0][1])
+
+
+# ------------------------------------------------------------------------------ boundary behaviour
+def test_host_entry_point_matches_device_entry_point(qr, ctx):
+    rng = np.random.default_rng(10)
+    A0 = rng.standard_normal((1024, 256), dtype=np.float32)
+    Qd, Rd = run_rgsqrf(qr, ctx, A0)
+    hA = torch.empty((256, 1024), dtype=torch.float32).pin_memory().t()
+    hA.copy_(torch.from_numpy(A0))
+    hR = torch.empty((256, 256), dtype=torch.float32).pin_memory().t()
+    qr.later_rgsqrf_host(ctx, 1024, 256, hA, 1024, hR, 256)
+    assert np.array_equal(hA.numpy(), Qd) and np.array_equal(hR.numpy(), Rd)
+
+
+def test_leading_dimensions_are_honoured(qr, ctx):
+    rng = np.random.default_rng(11)
+    A0 = rng.standard_normal((512, 256), dtype=np.float32)
+    Q1, R1 = run_rgsqrf(qr, ctx, A0)
+    A = qr.colmajor_empty(512, 256, ld=520)
+    A.copy_(torch.from_numpy(A0))
+    R = qr.colmajor_empty(256, 256, ld=300)
+    qr.later_rgsqrf(ctx, 512, 256, A, 520, R, 300)
+    assert np.array_equal(A.cpu().numpy(), Q1) and np.array_equal(R.cpu().numpy(), R1)
+
+
+def test_argument_errors_do_not_launch(qr, ctx):
+    A = qr.colmajor_empty(512, 192)
+    R = qr.colmajor_empty(192, 192)
+    with pytest.raises(qr.LaterError) as e:
+        qr.later_rgsqrf(ctx, 512, 192, A, 512, R, 192)          # n not a multiple of 128
+    assert e.value.code == -1
+    A = qr.colmajor_empty(128, 256)
+    R = qr.colmajor_empty(256, 256)
+    with pytest.raises(qr.LaterError):
+        qr.later_rgsqrf(ctx, 128, 256, A, 128, R, 256)          # m < n
+
+
+# ------------------------------------------------------------------------------ later_ormqr
+def test_ormqr_vs_oracle_and_reference(qr, ctx):
+    kind, m, n, dist, seed = CASES["ormqr_512x256"]
+    W0, Y0 = make_input(kind, m, n, dist, seed)
+    g = np.load(GOLD / "ormqr_512x256.npz")
+    for fn, key, of in ((qr.later_ormqr, "Q_ormqr", orc.later_ormqr), (qr.later_ormqr2, "Q_ormqr2", orc.later_ormqr2)):
+        W, Y = dev_colmajor(qr, W0), dev_colmajor(qr, Y0)
+        fn(m, n, W, m, Y, m, ctxt=ctx)
+        out = W.cpu().numpy()
+        ref64 = _ormqr_fp64(W0, Y0, merge=(key == "Q_ormqr"))
+        scale = np.abs(ref64).max()
+        # fp32-faithful: as close to the fp64 result as the reference's own fp32 cuBLAS path is
+        err_ref = np.abs(g[key].astype(np.float64) - ref64[::8, :]).max()
+        assert np.abs(out - ref64).max() <= max(4 * err_ref, 4e-6 * scale)
+        assert np.abs(out[::8, :] - g[key]).max() <= 1e-5 * scale
+
+
+def _ormqr_fp64(W0, Y0, merge):
+    W, Y = W0.astype(np.float64).copy(), Y0.astype(np.float64)
+    m, n = W.shape
+    h = n // 2
+    if merge:
+        W[:, h:] -= W[:, :h] @ (Y[:, :h].T @ W[:, h:])
+    return np.eye(m, n) - W @ Y[:n, :n].T
+
+
+def test_ormqr_large_is_fp32_faithful(qr, ctx):
+    m, n = 4096, 1024
+    g = torch.Generator(device="cuda").manual_seed(12)
+    Y0 = torch.tril(torch.randn(m, n, device="cuda", generator=g) * 0.05, -1)
+    Y0.diagonal().fill_(1.0)
+    W0 = torch.randn(m, n, device="cuda", generator=g) * 0.05
+    W, Y = qr.to_colmajor(W0), qr.to_colmajor(Y0)
+    qr.later_ormqr2(m, n, W, m, Y, m, ctxt=ctx)
+    ref = torch.eye(m, n, device="cuda", dtype=torch.float64) - W0.double() @ Y0.double()[:n, :n].t()
+    err = (W.double() - ref).abs().max().item() / ref.abs().max().item()
+    err32 = ((torch.eye(m, n, device="cuda") - W0 @ Y0[:n, :n].t()).double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= max(4 * err32, 2e-6)
+
+
+# ------------------------------------------------------------------------------ TSQR back-multiply
+def test_tsqr_apply(qr):
+    c = qr.Context()
+    g = torch.Generator(device="cuda").manual_seed(13)
+    A0 = torch.randn(8192, 256, device="cuda", generator=g)
+    Q, R = _factor_device(qr, c, A0)
+    W0 = torch.linalg.qr(torch.randn(256, 256, device="cuda", generator=g))[0]
+    W = qr.to_colmajor(W0)
+    Qbefore = Q.clone()
+    qr.tsqr_apply(c, 8192, 256, Q, 8192, W, 256)
+    ref = Qbefore.half().float() @ W0.half().float()
+    assert (Q - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    c.close()
+
+
+# ------------------------------------------------------------------------------ the reference's own driver
+def _parse_driver(out: str):
+    import re
+    orth = float(re.search(r"\|\|I-Q'\*Q\|\|/N = ([0-9.eE+-]+)", out).group(1))
+    back = float(re.search(r"Backward error: \|\|A-QR\|\|/\(\|\|A\|\|\) = ([0-9.eE+-]+)", out).group(1))
+    return back, orth
+
+
+@pytest.mark.parametrize("m,n", [(1024, 1024), (4096, 2048)])
+def test_reference_driver_runs_unchanged_against_this_library(m, n):
+    """test/test_qr.cu of the reference, compiled unmodified: once with the reference's own sources
+    (test_qr_ref) and once against later_b200 (test_qr_b200); same cuRAND input (seed 3000)."""
+    ref_bin, new_bin = ROOT / "oracle/_ref/test_qr_ref", ROOT / "oracle/_ref/test_qr_b200"
+    if not ref_bin.exists() or not new_bin.exists():
+        pytest.skip("oracle/_ref binaries not built (need /root/reference at build time)")
+    outs = []
+    for exe in (ref_bin, new_bin):
+        r = subprocess.run([str(exe), "1", str(m), str(n), "-check"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs.append(_parse_driver(r.stdout))
+    (back_ref, orth_ref), (back_new, orth_new) = outs
+    assert back_new <= 2 * back_ref and orth_new <= 2 * orth_ref, outs

@@ -1,0 +1,94 @@
+"""The oracle (oracle/rgsqrf_oracle.py, a numpy restatement of the reference) against
+ (1) outputs of the reference itself, generated on a B200 by tests/golden/make_golden.py from
+     oracle/_ref/libref_later.so and committed as fixtures - this is what pins the oracle;
+ (2) host LAPACK sgeqrf, the CPU stand-in BASELINE.json names;
+ (3) the structural facts the reference guarantees (R upper triangular, r_ii > 0, edge shapes)."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from oracle import rgsqrf_oracle as orc  # noqa: E402
+from tests.golden.make_golden import CASES, make_input  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+META = json.loads((GOLD / "golden_meta.json").read_text()) if (GOLD / "golden_meta.json").exists() else {}
+
+
+def _need(name):
+    if name not in META or not (GOLD / f"{name}.npz").exists():
+        pytest.fail(f"golden fixture {name} missing: run tests/golden/make_golden.py on the GPU box")
+    return np.load(GOLD / f"{name}.npz")
+
+
+@pytest.mark.parametrize("name", [k for k, v in CASES.items() if v[0] in ("panel", "rgsqrf")])
+def test_oracle_matches_reference_outputs(name):
+    kind, m, n, dist, seed = CASES[name]
+    g = _need(name)
+    A0 = make_input(kind, m, n, dist, seed)
+    if kind == "panel":
+        Q = np.array(A0, dtype=np.float32, order="F", copy=True)
+        R = np.zeros((n, n), dtype=np.float32)
+        orc.mgs_caqr_panel_256x128(Q, R)
+        tol = 2e-5          # pure fp32 path: differences are summation order only
+    else:
+        Q, R = orc.later_rgsqrf(A0)
+        tol = 2e-3          # fp16-rounded operands: a 1-ulp fp16 flip moves entries by ~5e-4 relative
+    scale = np.abs(g["R"]).max()
+    assert np.abs(np.triu(R) - np.triu(g["R"])).max() <= tol * scale
+    assert np.abs(Q[::8, :] - g["Q_rows8"]).max() <= tol * max(1.0, np.abs(g["Q_rows8"]).max())
+    # the driver's own metrics agree with the reference's to well within the 2x parity bar
+    back, orth = orc.check_result(A0, Q, R), orc.check_otho(Q)
+    assert back <= 1.5 * float(g["backward"]) + 1e-7
+    assert orth <= 1.5 * float(g["orth"]) + 1e-7
+
+
+def test_oracle_ormqr_matches_reference_outputs():
+    kind, m, n, dist, seed = CASES["ormqr_512x256"]
+    g = _need("ormqr_512x256")
+    W0, Y0 = make_input(kind, m, n, dist, seed)
+    q1 = orc.later_ormqr(W0, Y0)
+    q2 = orc.later_ormqr2(W0, Y0)
+    assert np.abs(q1[::8, :] - g["Q_ormqr"]).max() <= 1e-5 * max(1.0, np.abs(g["Q_ormqr"]).max())
+    assert np.abs(q2[::8, :] - g["Q_ormqr2"]).max() <= 1e-5 * max(1.0, np.abs(g["Q_ormqr2"]).max())
+
+
+@pytest.mark.parametrize("m,n,dist", [(512, 256, "normal"), (1024, 512, "uniform"), (384, 128, "normal")])
+def test_oracle_vs_lapack(m, n, dist):
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((m, n), dtype=np.float32) if dist == "normal" else rng.random((m, n), dtype=np.float32)
+    Q, R = orc.later_rgsqrf(A)
+    Ql, Rl = orc.lapack_qr(A)
+    # fp16-tensor-core tolerance vs LAPACK: backward error <= ~2 u_fp16
+    assert orc.check_result(A, Q, R) <= 1e-3
+    assert orc.check_result(A, Ql, Rl) <= 5e-6
+    # same factorisation up to rounding: diag(R) > 0 in both, R agrees at fp16 level scaled by cond
+    assert (np.diag(R) > 0).all()
+    cond = np.linalg.cond(A.astype(np.float64))
+    assert np.abs(R - Rl).max() <= 2e-3 * cond * np.abs(Rl).max()
+
+
+def test_oracle_structure_and_edge_shapes():
+    rng = np.random.default_rng(6)
+    # single-block panel (m == 256), ragged panel (m % 256 != 0), smallest legal square
+    for m, n in [(256, 128), (600, 128), (128, 128), (256, 256)]:
+        A = rng.standard_normal((m, n), dtype=np.float32)
+        Q, R = orc.later_rgsqrf(A)
+        assert Q.shape == (m, n) and R.shape == (n, n)
+        assert np.abs(np.tril(R, -1)).max() == 0.0
+        assert (np.diag(R) > 0).all()
+        assert orc.check_result(A, Q, R) < 1e-3
+    with pytest.raises(ValueError):
+        orc.later_rgsqrf(rng.standard_normal((256, 384), dtype=np.float32))   # n not 128*2^k, m < n
+    with pytest.raises(ValueError):
+        orc.later_rgsqrf(rng.standard_normal((100, 128), dtype=np.float32))   # m < n
+
+
+def test_fp16_cast_is_round_to_nearest_even():
+    x = np.array([1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, 65504.0, 1e-8], dtype=np.float32)
+    h = orc.s2h(x).astype(np.float32)
+    assert h[0] == 1.0 and h[1] == np.float32(1.0 + 2.0 ** -9) and h[2] == 65504.0 and h[3] == 0.0
