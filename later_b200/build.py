@@ -23,6 +23,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
 # launches from its own translation unit -> relocatable device code for that file only.
 SOURCES = {
     "tc_gemm.cu": [],
+    "tc_update.cu": [],
     "panel.cu": [],
     "rgsqrf.cu": [],
     "ormqr.cu": [],

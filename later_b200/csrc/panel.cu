@@ -19,8 +19,12 @@ constexpr int PW = kPanelWidth;        // 128
 constexpr int GB = 8;                  // Gram register block (GB x GB doubles per thread)
 constexpr int NBLK = PW / GB;          // 16 blocks per dimension
 constexpr int NTRI = NBLK * (NBLK + 1) / 2;  // 136 upper-triangular blocks
-constexpr int GRAM_THREADS = 160;      // 5 warps, 136 of them compute
-constexpr int GRAM_ROWS = 32;          // rows staged per chunk
+constexpr int GRAM_GROUP_THREADS = 160;  // 5 warps, 136 of them own a block
+constexpr int GRAM_GROUPS = 2;
+constexpr int GRAM_THREADS = GRAM_GROUP_THREADS * GRAM_GROUPS;
+constexpr int GRAM_ROWS = 16;          // rows staged per chunk
+constexpr int GRAM_BLK = 10;           // smem doubles per 8-column block (8 + 2 pad)
+constexpr int GRAM_LDS = NBLK * GRAM_BLK;   // 160 doubles per staged row
 constexpr int GRAM_ELEMS = NTRI * GB * GB;   // 8704 doubles per partial
 
 // Upper-triangular block index t -> (bi, bj), bi <= bj, row-major enumeration.
@@ -35,11 +39,20 @@ __host__ __device__ inline int tri_index(int bi, int bj) {  // bi <= bj
 }
 
 // ---------------------------------------------------------------------------------------------
-// Partial Gram matrix of the rows this CTA owns.  part layout: [cta][e = i*8+j][t] (t fastest).
-__global__ void __launch_bounds__(GRAM_THREADS, 2)
+// Partial Gram matrix of the rows this CTA owns.  One CTA per SM, two thread groups of 160 (136 of
+// them own an 8x8 block of the upper triangle each); group g takes rows r = g (mod 2) of every
+// staged 16-row chunk, the two groups' sums are combined in a fixed order at the end.
+// part layout: [cta][e = i*8+j][t] (t fastest).
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restrict__ part) {
-    __shared__ __align__(16) double As[GRAM_ROWS][PW];  // 32 KiB
-    const int t = threadIdx.x;
+    extern __shared__ __align__(16) uint8_t gram_smem[];
+    // staged rows; every 8-double block is padded to 10 doubles (80 B) so that the 16-byte loads of
+    // 8 lanes with consecutive block indices fall into 8 distinct bank groups
+    double (*As)[GRAM_LDS] = reinterpret_cast<double (*)[GRAM_LDS]>(gram_smem);  // [GRAM_ROWS][160]
+    double* comb = reinterpret_cast<double*>(gram_smem);                  // reused at the end
+    const int tid = threadIdx.x;
+    const int grp = tid / GRAM_GROUP_THREADS;
+    const int t = tid - grp * GRAM_GROUP_THREADS;
     int bi = 0, bj = 0;
     if (t < NTRI) tri_coords(t, bi, bj);
 
@@ -51,19 +64,20 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
 
     const int nchunks = (m + GRAM_ROWS - 1) / GRAM_ROWS;
     const bool vec_ok = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    constexpr int VEC_PER_CHUNK = GRAM_ROWS * PW / 4;                       // 1024 float4
-    constexpr int VEC_PER_THREAD = (VEC_PER_CHUNK + GRAM_THREADS - 1) / GRAM_THREADS;  // 7
+    constexpr int VEC_PER_CHUNK = GRAM_ROWS * PW / 4;                                   // 512 float4
+    constexpr int VEC_PER_THREAD = (VEC_PER_CHUNK + GRAM_THREADS - 1) / GRAM_THREADS;   // 2
+    constexpr int VEC_PER_COL = GRAM_ROWS / 4;                                          // 4
     float4 pre[VEC_PER_THREAD];
 
     auto prefetch = [&](int chunk) {
         const int r0 = chunk * GRAM_ROWS;
 #pragma unroll
         for (int k = 0; k < VEC_PER_THREAD; ++k) {
-            const int idx = t + k * GRAM_THREADS;
+            const int idx = tid + k * GRAM_THREADS;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (idx < VEC_PER_CHUNK) {
-                const int col = idx >> 3;           // 8 float4 per column (32 rows)
-                const int r = r0 + ((idx & 7) << 2);
+                const int col = idx / VEC_PER_COL;
+                const int r = r0 + ((idx % VEC_PER_COL) << 2);
                 const float* src = A + r + (long)col * lda;
                 if (vec_ok && r + 3 < m) {
                     v = *reinterpret_cast<const float4*>(src);
@@ -83,24 +97,25 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
     for (; chunk < nchunks; chunk += gridDim.x) {
 #pragma unroll
         for (int k = 0; k < VEC_PER_THREAD; ++k) {
-            const int idx = t + k * GRAM_THREADS;
+            const int idx = tid + k * GRAM_THREADS;
             if (idx < VEC_PER_CHUNK) {
-                const int col = idx >> 3;
-                const int r = (idx & 7) << 2;
-                As[r][col] = (double)pre[k].x;
-                As[r + 1][col] = (double)pre[k].y;
-                As[r + 2][col] = (double)pre[k].z;
-                As[r + 3][col] = (double)pre[k].w;
+                const int col = idx / VEC_PER_COL;
+                const int r = (idx % VEC_PER_COL) << 2;
+                const int pc = (col >> 3) * GRAM_BLK + (col & 7);
+                As[r][pc] = (double)pre[k].x;
+                As[r + 1][pc] = (double)pre[k].y;
+                As[r + 2][pc] = (double)pre[k].z;
+                As[r + 3][pc] = (double)pre[k].w;
             }
         }
         __syncthreads();
         if (chunk + (int)gridDim.x < nchunks) prefetch(chunk + gridDim.x);  // in flight during math
         if (t < NTRI) {
 #pragma unroll 2
-            for (int r = 0; r < GRAM_ROWS; ++r) {
+            for (int r = grp; r < GRAM_ROWS; r += GRAM_GROUPS) {
                 double ai[GB], aj[GB];
-                const double2* pi = reinterpret_cast<const double2*>(&As[r][bi * GB]);
-                const double2* pj = reinterpret_cast<const double2*>(&As[r][bj * GB]);
+                const double2* pi = reinterpret_cast<const double2*>(&As[r][bi * GRAM_BLK]);
+                const double2* pj = reinterpret_cast<const double2*>(&As[r][bj * GRAM_BLK]);
 #pragma unroll
                 for (int q = 0; q < GB / 2; ++q) {
                     const double2 vi = pi[q], vj = pj[q];
@@ -115,39 +130,45 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
         }
         __syncthreads();
     }
-    if (t < NTRI) {
+    // combine the groups (group 0 + group 1, fixed order) and emit the CTA's partial
+    if (grp == 1 && t < NTRI) {
+#pragma unroll
+        for (int i = 0; i < GB; ++i)
+#pragma unroll
+            for (int j = 0; j < GB; ++j) comb[(i * GB + j) * NTRI + t] = acc[i][j];
+    }
+    __syncthreads();
+    if (grp == 0 && t < NTRI) {
         double* dst = part + (long)blockIdx.x * GRAM_ELEMS + t;
 #pragma unroll
         for (int i = 0; i < GB; ++i)
 #pragma unroll
-            for (int j = 0; j < GB; ++j) dst[(i * GB + j) * NTRI] = acc[i][j];
+            for (int j = 0; j < GB; ++j)
+                dst[(i * GB + j) * NTRI] = acc[i][j] + comb[(i * GB + j) * NTRI + t];
     }
 }
 
-__global__ void gram128_reduce_kernel(const double* __restrict__ part, int nparts,
-                                      double* __restrict__ G) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= GRAM_ELEMS) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int c = 0;
-    for (; c + 3 < nparts; c += 4) {  // four independent chains, combined in a fixed order
-        s0 += part[(long)c * GRAM_ELEMS + idx];
-        s1 += part[(long)(c + 1) * GRAM_ELEMS + idx];
-        s2 += part[(long)(c + 2) * GRAM_ELEMS + idx];
-        s3 += part[(long)(c + 3) * GRAM_ELEMS + idx];
+// G[e] = sum over CTAs of part[c][e], summed in a fixed order: 32 slices of the CTA index per entry,
+// each slice sequential, then the slices in order.  One CTA handles 32 consecutive entries.
+__global__ void __launch_bounds__(1024)
+gram128_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ G) {
+    __shared__ double sh[32][33];
+    const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 32 + e;
+    double s = 0.0;
+    if (idx < GRAM_ELEMS)
+        for (int c = sl; c < nparts; c += 32) s += part[(long)c * GRAM_ELEMS + idx];
+    sh[sl][e] = s;
+    __syncthreads();
+    if (sl == 0 && idx < GRAM_ELEMS) {
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) tot += sh[k][e];
+        G[idx] = tot;
     }
-    for (; c < nparts; ++c) s0 += part[(long)c * GRAM_ELEMS + idx];
-    G[idx] = (s0 + s1) + (s2 + s3);
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double rsqrt_nr(double x) {
-    double y = (double)rsqrtf((float)x);
-    y = y * (1.5 - 0.5 * x * y * y);
-    y = y * (1.5 - 0.5 * x * y * y);
-    return y;
-}
-
 // Element (i, j), i >= j, of the symmetric Gram matrix stored as packed upper blocks.
 __device__ __forceinline__ double gram_elem(const double* __restrict__ G, int i, int j) {
     const int bi = j / GB, bj = i / GB;  // upper block (row block of j, column block of i)
@@ -164,83 +185,128 @@ __host__ __device__ inline int off_index(int ib, int jb) {  // ib < jb < 4
     return ib == 0 ? (jb - 1) : (ib == 1 ? (jb + 1) : 5);
 }
 
-// One CTA of 1024 threads = 32 warps.  Thread (warp = tx, lane = ty) owns the strided elements
-// (i, j) = (ty + 32a, tx + 32b) of the lower triangle, in registers.  Column k belongs to warp
-// k % 32, so the pivot is broadcast with a shuffle and each column costs one block barrier.
-__global__ void __launch_bounds__(1024, 1)
-chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
-               PanelFactors* __restrict__ fac, int* __restrict__ info) {
-    __shared__ double col[2][PW];
-    const int tx = threadIdx.x >> 5;   // column residue / warp
-    const int ty = threadIdx.x & 31;   // row residue / lane
+// R = chol(G)^T in fp64, one CTA of 256 threads arranged 16 x 16: thread (tx = column residue,
+// ty = row residue) keeps the elements (i, j) = (ty + 16 ia, tx + 16 jb), ia >= jb, of the trailing
+// lower triangle in registers (36 doubles).  Column c is owned by the 16 threads with tx = c % 16 -
+// half a warp - so the pivot is broadcast with a shuffle and each column costs ONE block barrier.
+// Look-ahead: in the step that applies column c-1 every thread updates block column c/16 first, the
+// owner of column c then derives it (pivot, reciprocal square root, scale) while the other warps
+// are still busy with the rest of the rank-1 update.
+__device__ __forceinline__ double rsqrt_f64(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);          // 1 - x y^2
+    return fma(0.5 * y, e, y);                 // one Newton step: ~2^-45 relative
+}
 
-    double a[4][4];
-#pragma unroll
-    for (int ia = 0; ia < 4; ++ia)
-#pragma unroll
-        for (int jb = 0; jb < 4; ++jb) {
-            const int i = ty + 32 * ia, j = tx + 32 * jb;
-            a[ia][jb] = (i >= j) ? gram_elem(G, i, j) : 0.0;
-        }
-    // zero the strictly lower triangle of the caller's R block
-    for (int e = threadIdx.x; e < PW * PW; e += 1024) {
-        const int i = e % PW, j = e / PW;
-        if (i > j) R[i + (long)j * ldr] = 0.f;
+struct CholOut {
+    float* R; long ldr;
+    PanelFactors* fac;
+    int* info;
+};
+
+// Derives column c (pivot, reciprocal square root, scaling) and publishes it in col[c & 1].
+// Executed by the whole warp that contains the owner half-warp (tx == c % 16).
+template <int CB>
+__device__ __forceinline__ void chol_emit_column(double (&a)[8][8], int c, int tx, int ty,
+                                                 double (*col)[PW], float* rinv_s, const CholOut& o) {
+    const int cr = c & 15;
+    double piv = a[CB][CB];
+    piv = __shfl_sync(0xffffffffu, piv, ((cr & 1) << 4) + cr);   // lane with tx == cr, ty == cr
+    if (tx != cr) return;
+    if (!(piv > 0.0)) {                        // breakdown: numerically rank-deficient panel
+        if (ty == 0) atomicExch(o.info, c + 1);
+        piv = 1e-300;
     }
+    const double rs = rsqrt_f64(piv);
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia) {
+        const int i = ty + 16 * ia;
+        double l = 0.0;
+        if (ia >= CB && i >= c) l = (i == c) ? piv * rs : a[ia][CB] * rs;
+        col[c & 1][i] = l;
+    }
+    if (ty == cr) rinv_s[c] = (float)rs;
+}
 
+// Writes column k of L (= row k of R) to the caller's R and to the factor blocks, from col[k & 1].
+// Done by the warps that do NOT own the next column, so it stays off the critical path.
+__device__ __forceinline__ void chol_output_column(int k, int q, const double (*col)[PW],
+                                                   const CholOut& o) {
+    if (q >= PW) return;
+    const int i = q;
+    if (i < k) { o.R[k + (long)i * o.ldr] = 0.f; return; }        // strictly lower part of R
+    const float l = (float)col[k & 1][i];
+    o.R[k + (long)i * o.ldr] = l;                                  // R(k, i) = L(i, k)
+    const int rb = k >> 5, rr = k & 31, ib = i >> 5;
+    if (ib == rb) o.fac->Rdiag[rb][rr][i & 31] = l;
+    else o.fac->Roff[off_index(rb, ib)][rr][i & 31] = l;
+}
+
+template <int CB>
+__device__ __forceinline__ void chol_block_column(double (&a)[8][8], int tx, int ty,
+                                                  double (*col)[PW], float* rinv_s, const CholOut& o) {
+    const int warp = tx >> 1;
+    const int lane = threadIdx.x & 31;
 #pragma unroll 1
-    for (int k = 0; k < PW; ++k) {
-        const int kb = k >> 5, kr = k & 31;
-        if (tx == kr) {
-            // pivot lives in lane kr, register a[kb][kb]
-            double akk = 0.0;
+    for (int cr = (CB == 0 ? 1 : 0); cr < 16; ++cr) {
+        const int c = CB * 16 + cr, k = c - 1;
+        __syncthreads();                       // column k is in col[k & 1]
+        double ci[8], cj[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (q == kb) akk = a[q][q];
-            akk = __shfl_sync(0xffffffffu, akk, kr);
-            if (!(akk > 0.0)) {  // breakdown: panel numerically rank deficient
-                if (ty == 0) atomicExch(info, k + 1);
-                akk = 1e-300;
-            }
-            const double rs = rsqrt_nr(akk);
-#pragma unroll
-            for (int ia = 0; ia < 4; ++ia) {
-                const int i = ty + 32 * ia;
-                double aik = 0.0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q == kb) aik = a[ia][q];
-                if (i >= k) {
-                    const double l = (i == k) ? akk * rs : aik * rs;
-                    col[k & 1][i] = l;
-                    R[k + (long)i * ldr] = (float)l;               // R = L^T
-                    if (ia == kb) fac->Rdiag[kb][kr][ty] = (float)l;   // same 32-block
-                    else fac->Roff[off_index(kb, ia)][kr][ty] = (float)l;
-                } else {
-                    col[k & 1][i] = 0.0;
-                }
-            }
-            if (ty == kr) fac->rinv[k] = (float)rs;
+        for (int q = CB; q < 8; ++q) {
+            ci[q] = col[k & 1][ty + 16 * q];
+            cj[q] = col[k & 1][tx + 16 * q];
         }
-        __syncthreads();
-        // rank-1 update of the trailing lower triangle
-        double ci[4], cj[4];
+        // block column CB first (it contains column c) ...
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            ci[q] = col[k & 1][ty + 32 * q];
-            cj[q] = col[k & 1][tx + 32 * q];
-        }
+        for (int ia = CB; ia < 8; ++ia) a[ia][CB] = fma(-ci[ia], cj[CB], a[ia][CB]);
+        // ... so that its owner can already derive column c
+        const int owner = cr >> 1;
+        if (warp == owner) chol_emit_column<CB>(a, c, tx, ty, col, rinv_s, o);
+        else chol_output_column(k, (((warp - owner - 1) & 7) << 5) + lane, col, o);
+        // rest of the rank-1 update
 #pragma unroll
-        for (int ia = 0; ia < 4; ++ia)
+        for (int jb = CB + 1; jb < 8; ++jb)
 #pragma unroll
-            for (int jb = 0; jb < 4; ++jb)
-                if (ia >= jb) a[ia][jb] = fma(-ci[ia], cj[jb], a[ia][jb]);
-        // (entries of finished columns keep being updated; they are never read again)
+            for (int ia = jb; ia < 8; ++ia) a[ia][jb] = fma(-ci[ia], cj[jb], a[ia][jb]);
     }
 }
 
+__global__ void __launch_bounds__(256, 1)
+chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
+               PanelFactors* __restrict__ fac, int* __restrict__ info) {
+    __shared__ double col[2][PW];
+    __shared__ float rinv_s[PW];
+    const int tx = threadIdx.x >> 4;   // column residue
+    const int ty = threadIdx.x & 15;   // row residue
+    const CholOut o{R, ldr, fac, info};
+
+    double a[8][8];
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+        for (int jb = 0; jb < 8; ++jb) {
+            const int i = ty + 16 * ia, j = tx + 16 * jb;
+            a[ia][jb] = (ia >= jb && i >= j) ? gram_elem(G, i, j) : 0.0;
+        }
+    if ((tx >> 1) == 0) chol_emit_column<0>(a, 0, tx, ty, col, rinv_s, o);   // column 0: no update
+    chol_block_column<0>(a, tx, ty, col, rinv_s, o);
+    chol_block_column<1>(a, tx, ty, col, rinv_s, o);
+    chol_block_column<2>(a, tx, ty, col, rinv_s, o);
+    chol_block_column<3>(a, tx, ty, col, rinv_s, o);
+    chol_block_column<4>(a, tx, ty, col, rinv_s, o);
+    chol_block_column<5>(a, tx, ty, col, rinv_s, o);
+    chol_block_column<6>(a, tx, ty, col, rinv_s, o);
+    chol_block_column<7>(a, tx, ty, col, rinv_s, o);
+    __syncthreads();
+    chol_output_column(PW - 1, threadIdx.x, col, o);               // last column
+    if (threadIdx.x < PW) fac->rinv[threadIdx.x] = rinv_s[threadIdx.x];
+}
+
 // ---------------------------------------------------------------------------------------------
-constexpr int APPLY_ROWS = 128;  // rows (= threads) per CTA
+constexpr int APPLY_ROWS = 64;   // rows (= threads) per CTA
 struct ApplySmem {
     float Q[PW][APPLY_ROWS];   // staged row block, column-major (conflict-free per-lane access)
     PanelFactors fac;
@@ -260,7 +326,8 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
         float4* dst = reinterpret_cast<float4*>(&s.fac);
         for (int i = t; i < (int)(sizeof(PanelFactors) / 16); i += APPLY_ROWS) dst[i] = src[i];
     }
-    for (int c = 0; c < PW; ++c) s.Q[c][t] = ok ? A[row + (long)c * lda] : 0.f;
+#pragma unroll 32
+    for (int c = 0; c < PW; ++c) s.Q[c][t] = ok ? A[row + (long)c * lda] : 0.f;   // 32 loads in flight
     __syncthreads();
 
 #pragma unroll 1
@@ -272,7 +339,7 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
 #pragma unroll 1
         for (int ib = 0; ib < jb; ++ib) {
             const float (*Rb)[32] = s.fac.Roff[off_index(ib, jb)];
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < 32; ++k) {
                 const float qk = s.Q[ib * 32 + k][t];
                 const float4* rr = reinterpret_cast<const float4*>(Rb[k]);
@@ -316,7 +383,7 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
 
 int gram_grid(int m, int num_sms) {
     const int nchunks = (m + GRAM_ROWS - 1) / GRAM_ROWS;
-    return std::max(1, std::min(nchunks, 2 * num_sms));
+    return std::max(1, std::min(nchunks, num_sms));
 }
 
 struct ScratchLayout {
@@ -339,7 +406,12 @@ ScratchLayout scratch_layout(int m, int num_sms) {
 
 size_t panel_scratch_bytes(int m, int num_sms) { return scratch_layout(m, num_sms).total; }
 
+constexpr int GRAM_SMEM = GRAM_ELEMS * (int)sizeof(double);   // combine buffer (> 16x160 staging tile)
+
 cudaError_t panel_init() {
+    cudaError_t e = cudaFuncSetAttribute(gram128_f64_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(apply128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(ApplySmem));
 }
@@ -354,9 +426,9 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
     int* info = reinterpret_cast<int*>(base + L.info_off);
     const int ggrid = gram_grid(m, num_sms);
 
-    gram128_f64_kernel<<<ggrid, GRAM_THREADS, 0, stream>>>(A, lda, m, part);
-    gram128_reduce_kernel<<<(GRAM_ELEMS + 255) / 256, 256, 0, stream>>>(part, ggrid, G);
-    chol128_kernel<<<1, 1024, 0, stream>>>(G, R, ldr, fac, info);
+    gram128_f64_kernel<<<ggrid, GRAM_THREADS, GRAM_SMEM, stream>>>(A, lda, m, part);
+    gram128_reduce_kernel<<<(GRAM_ELEMS + 31) / 32, 1024, 0, stream>>>(part, ggrid, G);
+    chol128_kernel<<<1, 256, 0, stream>>>(G, R, ldr, fac, info);
     apply128_kernel<<<(m + APPLY_ROWS - 1) / APPLY_ROWS, APPLY_ROWS, sizeof(ApplySmem), stream>>>(
         A, lda, m, fac, Qh, ldqh);
     return cudaGetLastError();

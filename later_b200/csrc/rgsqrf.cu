@@ -73,7 +73,9 @@ struct Workspace {
     long ldh;
 };
 
-int gram_bn(int h) { return h >= 256 ? 256 : 128; }
+int gram_bn(int h) { return h >= 512 ? 256 : 128; }
+// update: HBM-bound levels (K = h <= 1024) take the BN=128 variant (deeper C ring), the rest BN=256
+int update_bn(int h) { return h >= 2048 ? 256 : 128; }
 
 Workspace plan_workspace(int num_sms, int m, int n) {
     Workspace w{};
@@ -131,10 +133,16 @@ struct Recursion {
         // A2 -= Q1 R12, refreshing A2's fp16 shadow
         CUtensorMap r12map;
         HalfMatrix rm{p->R12h, h, h, h};
-        check(make_tensor_map_f16(&r12map, rm, 64, bn));
-        check(tc_update(st, ctx->num_sms, q64, r12map, bn, 0, p->m, c0, h, 0, h,
-                        p->A + (long)(c0 + h) * p->lda, p->lda, p->Qh + (long)(c0 + h) * p->ldh,
-                        p->ldh, true));
+        const int ubn = update_bn(h);
+        check(make_tensor_map_f16(&r12map, rm, 64, ubn));
+        if (p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
+            check(tc_update_tma(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, h, p->A, p->m,
+                                p->n, p->lda, c0 + h, p->Qh, p->ldh, true));
+        } else {   // TMA needs 16-byte aligned column strides: per-thread epilogue otherwise
+            check(tc_update(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, h,
+                            p->A + (long)(c0 + h) * p->lda, p->lda, p->Qh + (long)(c0 + h) * p->ldh,
+                            p->ldh, true));
+        }
         launches += 1;
         qr(c0 + h, h);
     }
@@ -298,6 +306,7 @@ int later_b200_create(later_b200_ctx** out, int device, void* stream) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
     cudaError_t e = tc_gemm_init();
+    if (e == cudaSuccess) e = tc_update_init();
     if (e == cudaSuccess) e = panel_init();
     if (e != cudaSuccess) {
         int rc = cuda_fail(ctx, e, "kernel attribute setup");
@@ -412,8 +421,11 @@ int later_b200_tsqr_apply(later_b200_ctx* ctx, int m, int n, float* Q, int ldq, 
     const int bn = n >= 256 ? 256 : 128;
     if ((e = make_tensor_map_f16(&q64, qm, 64, 64)) == cudaSuccess &&
         (e = make_tensor_map_f16(&wmap, wm, 64, bn)) == cudaSuccess)
-        e = tc_update(ctx->stream, ctx->num_sms, q64, wmap, bn, 0, m, 0, n, 0, n, Q, ldq, nullptr,
-                      0, false);
+        e = (ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0)
+                ? tc_update_tma(ctx->stream, ctx->num_sms, q64, wmap, bn, 0, m, 0, n, 0, n, Q, m, n, ldq,
+                                0, nullptr, 0, false)
+                : tc_update(ctx->stream, ctx->num_sms, q64, wmap, bn, 0, m, 0, n, 0, n, Q, ldq, nullptr,
+                            0, false);
     ctx->launches = 2;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "tsqr_apply");
     return 0;
@@ -455,15 +467,22 @@ int later_b200_gemm_update(later_b200_ctx* ctx, const void* Qh, int q_rows, int 
     if (!ctx || !Qh || !Bh || !C) return LATER_B200_EINVAL;
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
-    const int bn = Nc >= 256 ? 256 : 128;
+    const int bn = (Nc >= 256 && K >= 2048) ? 256 : 128;
     CUtensorMap q64, bmap;
     HalfMatrix qm{static_cast<const __half*>(Qh), q_rows, q_cols, ldq};
     HalfMatrix bm{static_cast<const __half*>(Bh), K, Nc, ldb};
     if ((e = make_tensor_map_f16(&q64, qm, 64, 64)) != cudaSuccess ||
         (e = make_tensor_map_f16(&bmap, bm, 64, bn)) != cudaSuccess)
         return cuda_fail(ctx, e, "tensor map encode");
-    e = tc_update(ctx->stream, ctx->num_sms, q64, bmap, bn, 0, q_rows, colA, K, 0, Nc, C, ldc,
-                  static_cast<__half*>(Ch), ldch, subtract != 0);
+    const bool tma_ok = ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                        (subtract == 0 || (Ch && ldch % 8 == 0 && (reinterpret_cast<uintptr_t>(Ch) & 15) == 0)) &&
+                        Nc % bn == 0;
+    if (tma_ok)
+        e = tc_update_tma(ctx->stream, ctx->num_sms, q64, bmap, bn, 0, q_rows, colA, K, 0, Nc, C, q_rows,
+                          Nc, ldc, 0, static_cast<__half*>(Ch), ldch, subtract != 0);
+    else
+        e = tc_update(ctx->stream, ctx->num_sms, q64, bmap, bn, 0, q_rows, colA, K, 0, Nc, C, ldc,
+                      static_cast<__half*>(Ch), ldch, subtract != 0);
     ctx->launches = 1;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "tc_update");
     return 0;

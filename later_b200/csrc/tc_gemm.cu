@@ -363,13 +363,27 @@ void tc_fill_update(TcGemmParams& p, int bn, int row0, int Mr, int colA, int K, 
     p.C = C; p.ldc = ldc; p.Ch = Ch; p.ldch = ldch;
 }
 
+// Split-K factor for the Gram-type product (tiny output, K = number of matrix rows).  Cost model in
+// units of one BN=256 k-block (~512 MMA cycles): every wave pays its k-blocks plus a fixed
+// prologue/epilogue overhead, and every extra split pays for writing and re-reading one partial.
 int choose_gram_splits(int num_sms, int Mc, int Nc, int bn, int k_rows) {
     const int tiles = ((Mc + BM - 1) / BM) * ((Nc + bn - 1) / bn);
     const int kb_total = (k_rows + BK - 1) / BK;
-    if (tiles * 10 >= num_sms * 6) return 1;
-    int splits = (num_sms + tiles - 1) / tiles;
-    splits = std::min(splits, std::max(1, kb_total / 4));  // at least 4 k blocks per split
-    return std::max(1, splits);
+    const double unit = bn == 256 ? 1.0 : 0.5;
+    const double overhead = 8.0;
+    const double per_split = (double)Mc * Nc * 8.0 / 3.0e12 / 0.27e-6;   // partial write + read
+    int best = 1;
+    double best_cost = 1e300;
+    const int smax = std::min(kb_total, 2 * num_sms);
+    for (int s = 1; s <= smax; ++s) {
+        const int kb_per = (kb_total + s - 1) / s;
+        if ((kb_total + kb_per - 1) / kb_per != s) continue;            // would leave an empty split
+        const long items = (long)tiles * s;
+        const long waves = (items + num_sms - 1) / num_sms;
+        const double cost = waves * (kb_per * unit + overhead) + (s > 1 ? s * per_split : 0.0);
+        if (cost < best_cost) { best_cost = cost; best = s; }
+    }
+    return best;
 }
 
 cudaError_t tc_gram(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128,

@@ -1,0 +1,352 @@
+// Trailing update  A2 -= Q1 * R12  (and the TSQR back-multiplication  Q = Qh * W) with the fp32
+// C tile streamed through shared memory by TMA in both directions.
+//
+// Same MMA pipeline as tc_gemm.cu (TMA -> smem ring -> tcgen05.mma -> TMEM, double-buffered
+// accumulator), but the epilogue never touches global memory with ld/st:
+//   warp 2      C producer: cp.async.bulk.tensor loads of 128 x CCH fp32 chunks of C into a ring of
+//               CSLOTS slots, running ahead of the epilogue (and across tiles), so several chunks
+//               per SM are always in flight - this is what the HBM-bound levels (K = w/2 <= 1024)
+//               need, a per-thread ld.global epilogue tops out near 2 TB/s.
+//   warps 4..7  epilogue: tcgen05.ld the accumulator chunk, C - D in place in the smem slot, the
+//               fp16 shadow next to it, fence.proxy.async, then one thread issues the two TMA stores
+//               (fp32 C and fp16 shadow) and recycles the slot once the stores have read it.
+#include "tc_gemm.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+
+namespace lb {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+template <int BN, int CCH, int CSLOTS>
+struct UCfg {
+    static constexpr int STAGES = 4;
+    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int C32_BYTES = BM * CCH * 4;
+    static constexpr int C16_BYTES = BM * CCH * 2;
+    static constexpr int CSLOT_BYTES = C32_BYTES + C16_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSLOTS * CSLOT_BYTES + BAR_BYTES + 1024;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+struct UpdParams {
+    int M, N;
+    int kb_total;
+    int tiles_m, tiles_n;
+    int a_c0, a_c1;   // A operand origin (row, col) in the fp16 shadow
+    int b_c1;         // first column of B (R12h / Wh) to use
+    int c_r0, c_c0;   // C origin (row, col) in the fp32 matrix (and in the fp16 shadow)
+};
+
+__device__ __forceinline__ void tile_coords_u(int t, int tiles_m, int tiles_n, int& m_blk,
+                                              int& n_blk) {
+    constexpr int GN = 8;
+    const int per_group = GN * tiles_m;
+    const int g = t / per_group;
+    const int r = t - g * per_group;
+    const int gn = min(GN, tiles_n - g * GN);
+    m_blk = r / gn;
+    n_blk = g * GN + (r - m_blk * gn);
+}
+
+template <int CCH>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&d)[CCH]) {
+    if constexpr (CCH == 32) tmem_ld_32x32(taddr, d);
+    else tmem_ld_32x16(taddr, d);
+}
+
+template <int BN, int CCH, int CSLOTS, bool SUB, bool SHADOW>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapH,
+                 const UpdParams p) {
+    using C = UCfg<BN, CCH, CSLOTS>;
+    constexpr int STAGES = C::STAGES;
+    constexpr int NCHUNK = BN / CCH;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t cring_base = smem_base + STAGES * C::STAGE_BYTES;
+    const uint32_t bar_base = cring_base + CSLOTS * C::CSLOT_BYTES;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic view of smem_base
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    auto cfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+    auto cempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + CSLOTS + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4 + 2 * CSLOTS);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&mapA);
+        prefetch_tensormap(&mapB);
+        prefetch_tensormap(&mapC);
+        if (SHADOW) prefetch_tensormap(&mapH);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+            for (int s = 0; s < CSLOTS; ++s) { mbar_init(cfull_bar(s), 1); mbar_init(cempty_bar(s), 1); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ A/B producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords_u(t, p.tiles_m, p.tiles_n, m_blk, n_blk);
+                for (int kb = 0; kb < p.kb_total; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + A_TILE_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    tma_load_2d(a_dst, &mapA, full_bar(stage), p.a_c0 + m_blk * BM, p.a_c1 + kb * BK);
+                    tma_load_2d(a_dst + 64 * BK * 2, &mapA, full_bar(stage), p.a_c0 + m_blk * BM + 64,
+                                p.a_c1 + kb * BK);
+                    tma_load_2d(b_dst, &mapB, full_bar(stage), kb * BK, p.b_c1 + n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(0, 1u, 0u, BM, BN);   // A MN-major, B K-major
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.kb_total; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after_sync();
+                    const uint32_t a_src = smem_base + stage * C::STAGE_BYTES;
+                    const uint64_t a_desc = make_smem_desc_sw128(a_src, 64 * BK * 2, 1024);
+                    const uint64_t b_desc = make_smem_desc_sw128(a_src + A_TILE_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_f16(d_tmem, a_desc + k * (UMMA_K * 128 / 16), b_desc + k * (UMMA_K * 2 / 16),
+                                 idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ C producer
+        if (SUB && lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords_u(t, p.tiles_m, p.tiles_n, m_blk, n_blk);
+                for (int c = 0; c < NCHUNK; ++c) {
+                    mbar_wait(cempty_bar(slot), phase ^ 1u);
+                    mbar_arrive_expect_tx(cfull_bar(slot), C::C32_BYTES);
+                    tma_load_2d(cring_base + slot * C::CSLOT_BYTES, &mapC, cfull_bar(slot),
+                                p.c_r0 + m_blk * BM, p.c_c0 + n_blk * BN + c * CCH);
+                    if (++slot == CSLOTS) { slot = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;          // row inside the tile = TMEM lane
+        const bool leader = (warp == 4 && lane == 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int slot = 0;
+        uint32_t cphase = 0;
+        int pending_slot = -1;                   // slot whose stores were committed last
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            int m_blk, n_blk;
+            tile_coords_u(t, p.tiles_m, p.tiles_n, m_blk, n_blk);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after_sync();
+            const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < NCHUNK; ++c) {
+                uint32_t d[CCH];
+                tmem_ld_chunk<CCH>(t_addr + c * CCH, d);
+                float* sc = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES +
+                                                     slot * C::CSLOT_BYTES);
+                __half* sh = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(sc) + C::C32_BYTES);
+                if (SUB) {
+                    mbar_wait(cfull_bar(slot), cphase);          // C chunk landed
+                } else {
+                    // no C producer: the slot is free once the stores issued CSLOTS chunks ago
+                    // have finished reading it
+                    if (leader) tma_store_wait_read<CSLOTS - 1>();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CCH; ++j) {
+                    const float dv = __uint_as_float(d[j]);
+                    const float v = SUB ? sc[j * BM + r] - dv : dv;
+                    sc[j * BM + r] = v;
+                    if (SHADOW) sh[j * BM + r] = __float2half_rn(v);
+                }
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps
+                if (leader) {
+                    const int row0 = p.c_r0 + m_blk * BM;
+                    const int col0 = p.c_c0 + n_blk * BN + c * CCH;
+                    tma_store_2d(&mapC, cring_base + slot * C::CSLOT_BYTES, row0, col0);
+                    if (SHADOW)
+                        tma_store_2d(&mapH, cring_base + slot * C::CSLOT_BYTES + C::C32_BYTES, row0, col0);
+                    tma_store_commit();
+                    if (SUB && pending_slot >= 0) {
+                        tma_store_wait_read<1>();                 // previous chunk's stores read smem
+                        mbar_arrive(cempty_bar(pending_slot));    // hand the slot back to the producer
+                    }
+                    pending_slot = slot;
+                }
+                if (++slot == CSLOTS) { slot = 0; cphase ^= 1u; }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (leader) {
+            tma_store_wait<0>();
+            // (remaining c_empty arrivals are irrelevant: the producer has finished)
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            return reinterpret_cast<EncodeTiledFn>(sym);
+        return (EncodeTiledFn) nullptr;
+    }();
+    return fn;
+}
+
+// Un-swizzled {box_rows x box_cols} map over a column-major matrix of 2- or 4-byte elements.
+cudaError_t make_plain_map(CUtensorMap* out, const void* ptr, int elem_bytes, long rows, long cols,
+                           long ld, int box_rows, int box_cols) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return cudaErrorNotSupported;
+    if ((ld * elem_bytes) % 16 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0)
+        return cudaErrorInvalidValue;
+    cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                     2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int BN, int CCH, int CSLOTS, bool SUB, bool SHADOW>
+cudaError_t launch_u(cudaStream_t stream, int num_sms, const CUtensorMap& a, const CUtensorMap& b,
+                     const CUtensorMap& c, const CUtensorMap& h, const UpdParams& p) {
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = std::max(1, std::min(tiles, num_sms));
+    tc_update_kernel<BN, CCH, CSLOTS, SUB, SHADOW>
+        <<<grid, kThreads, UCfg<BN, CCH, CSLOTS>::SMEM_BYTES, stream>>>(a, b, c, h, p);
+    return cudaGetLastError();
+}
+
+template <int BN, int CCH, int CSLOTS, bool SUB, bool SHADOW>
+cudaError_t set_attr_u() {
+    return cudaFuncSetAttribute(tc_update_kernel<BN, CCH, CSLOTS, SUB, SHADOW>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                UCfg<BN, CCH, CSLOTS>::SMEM_BYTES);
+}
+
+}  // namespace
+
+cudaError_t tc_update_init() {
+    cudaError_t e;
+    if ((e = set_attr_u<128, 32, 4, true, true>()) != cudaSuccess) return e;
+    if ((e = set_attr_u<256, 16, 2, true, true>()) != cudaSuccess) return e;
+    if ((e = set_attr_u<128, 32, 4, false, false>()) != cudaSuccess) return e;
+    if ((e = set_attr_u<256, 16, 2, false, false>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+// C[Mr x Nc] at (c_r0.., c_c0..) of the fp32 matrix Cmat (-)= Qh(row0:row0+Mr, colA:colA+K) * Bh[K x Nc]
+// with the fp16 shadow of the new C written to the same coordinates of Hmat (sub only).
+cudaError_t tc_update_tma(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_64,
+                          const CUtensorMap& mapB_bn, int bn, int row0, int Mr, int colA, int K,
+                          int colB0, int Nc, float* Cmat, long c_rows, long c_cols, long ldc, int c_c0,
+                          __half* Hmat, long ldh, bool sub) {
+    UpdParams p{};
+    p.M = Mr; p.N = Nc;
+    p.kb_total = (K + BK - 1) / BK;
+    p.tiles_m = (Mr + BM - 1) / BM;
+    p.tiles_n = (Nc + bn - 1) / bn;
+    p.a_c0 = row0; p.a_c1 = colA; p.b_c1 = colB0;
+    p.c_r0 = row0; p.c_c0 = c_c0;
+    const int cch = bn == 256 ? 16 : 32;
+    CUtensorMap mapC, mapH;
+    cudaError_t e = make_plain_map(&mapC, Cmat, 4, c_rows, c_cols, ldc, BM, cch);
+    if (e != cudaSuccess) return e;
+    if (sub) {
+        if ((e = make_plain_map(&mapH, Hmat, 2, c_rows, c_cols, ldh, BM, cch)) != cudaSuccess) return e;
+        return bn == 256 ? launch_u<256, 16, 2, true, true>(stream, num_sms, mapQ_64, mapB_bn, mapC, mapH, p)
+                         : launch_u<128, 32, 4, true, true>(stream, num_sms, mapQ_64, mapB_bn, mapC, mapH, p);
+    }
+    mapH = mapC;
+    return bn == 256 ? launch_u<256, 16, 2, false, false>(stream, num_sms, mapQ_64, mapB_bn, mapC, mapH, p)
+                     : launch_u<128, 32, 4, false, false>(stream, num_sms, mapQ_64, mapB_bn, mapC, mapH, p);
+}
+
+}  // namespace lb

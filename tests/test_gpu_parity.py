@@ -186,13 +186,16 @@ def test_full_size_properties(qr, ctx, m, n, dist, back_max, orth_max):
     assert abs(float(torch.linalg.norm(R.double()) / torch.linalg.norm(A0.double())) - 1.0) <= 1e-2
 
 
-def test_scaling_by_powers_of_two_is_exact(qr, ctx):
-    """Linearity: QR(4 A) = Q (4 R) bit for bit - every operation commutes with power-of-two scaling."""
+def test_scaling_by_powers_of_two(qr, ctx):
+    """Linearity: QR(4 A) = Q (4 R).  Every operation commutes with power-of-two scaling except
+    the fp16 casts of entries below the fp16 normal range (|x| < 6.1e-5), so the two runs agree to
+    far better than the algorithm's own fp16-level accuracy, but not bit for bit."""
     g = torch.Generator(device="cuda").manual_seed(7)
     A0 = torch.randn(2048, 512, device="cuda", generator=g)
     Q1, R1 = _factor_device(qr, ctx, A0)
     Q2, R2 = _factor_device(qr, ctx, A0 * 4.0)
-    assert torch.equal(Q1, Q2) and torch.equal(R1 * 4.0, R2)
+    assert (Q1 - Q2).abs().max().item() <= 1e-5
+    assert (R1 * 4.0 - R2).abs().max().item() <= 1e-5 * R2.abs().max().item()
 
 
 def test_requantising_q_is_idempotent(qr, ctx):
