@@ -2,30 +2,36 @@
 //   gram128_f64_kernel    one pass over the panel: all column norms and dot products, exact
 //                         fp32 x fp32 products accumulated in fp64, per-CTA partial Gram blocks
 //   gram128_reduce_kernel fixed-order sum of the per-CTA partials (deterministic)
-//   chol128_kernel        R = chol(G) in fp64 (one CTA, register-resident trailing matrix, one
-//                         block barrier per column), emits R (fp32) and its 32x32 blocks
-//   apply128_kernel       Q = A R^-1, one matrix row per thread, forward substitution (project
-//                         out earlier 32-column blocks, then solve against the diagonal block);
-//                         writes Q (fp32, in place) and its fp16 shadow
+//   chol128_kernel        R = chol(G) in fp64 on one CTA: trailing matrix in registers, columns
+//                         broadcast through an mbarrier-guarded shared-memory ring (no block-wide
+//                         barrier on the critical path); publishes R block-row by block-row
+//   apply128_kernel       Q = A R^-1 by forward substitution, four threads per matrix row; launched
+//                         with programmatic dependent launch so that it runs CONCURRENTLY with the
+//                         Cholesky kernel and consumes each 32-row block of R as soon as its flag is
+//                         raised; writes Q (fp32, in place) and its fp16 shadow
 #include "panel.cuh"
+#include "ptx.cuh"
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 
 namespace lb {
 namespace {
+
+using namespace ptx;
 
 constexpr int PW = kPanelWidth;        // 128
 constexpr int GB = 8;                  // Gram register block (GB x GB doubles per thread)
 constexpr int NBLK = PW / GB;          // 16 blocks per dimension
 constexpr int NTRI = NBLK * (NBLK + 1) / 2;  // 136 upper-triangular blocks
-constexpr int GRAM_GROUP_THREADS = 160;  // 5 warps, 136 of them own a block
+constexpr int GRAM_GROUP_THREADS = 144;  // 136 of them own a block
 constexpr int GRAM_GROUPS = 2;
-constexpr int GRAM_THREADS = GRAM_GROUP_THREADS * GRAM_GROUPS;
+constexpr int GRAM_THREADS = GRAM_GROUP_THREADS * GRAM_GROUPS;   // 288
 constexpr int GRAM_ROWS = 16;          // rows staged per chunk
 constexpr int GRAM_BLK = 10;           // smem doubles per 8-column block (8 + 2 pad)
 constexpr int GRAM_LDS = NBLK * GRAM_BLK;   // 160 doubles per staged row
-constexpr int GRAM_ELEMS = NTRI * GB * GB;   // 8704 doubles per partial
+constexpr int GRAM_ELEMS = NTRI * GB * GB;  // 8704 doubles per partial
 
 // Upper-triangular block index t -> (bi, bj), bi <= bj, row-major enumeration.
 __host__ __device__ inline void tri_coords(int t, int& bi, int& bj) {
@@ -38,17 +44,32 @@ __host__ __device__ inline int tri_index(int bi, int bj) {  // bi <= bj
     return bi * NBLK - bi * (bi - 1) / 2 + (bj - bi);
 }
 
+// Factors handed from the Cholesky kernel to the apply kernel.  Columns inside a 32-wide block are
+// stored permuted, perm(c) = (c % 4) * 8 + c / 4, so that the apply thread that owns the columns
+// c = p (mod 4) reads its 8 entries of a row with two 16-byte loads.
+struct PanelFactors {
+    float Roff[6][32][32];   // off-diagonal blocks R(ib, jb), ib < jb: [k][perm(c)]
+    float Rdiag[4][32][32];  // diagonal blocks R(b, b): [k][perm(c)], only c >= k is defined
+    float rinv[128];         // 1 / R(c, c)
+    int flag[4];             // flag[b] = 1 once block-row b of R (and rinv) is complete
+    int pad[28];
+};
+__host__ __device__ inline int off_index(int ib, int jb) {  // ib < jb < 4
+    return ib == 0 ? (jb - 1) : (ib == 1 ? (jb + 1) : 5);
+}
+__host__ __device__ inline int perm32(int c) { return ((c & 3) << 3) | (c >> 2); }
+
 // ---------------------------------------------------------------------------------------------
-// Partial Gram matrix of the rows this CTA owns.  One CTA per SM, two thread groups of 160 (136 of
-// them own an 8x8 block of the upper triangle each); group g takes rows r = g (mod 2) of every
-// staged 16-row chunk, the two groups' sums are combined in a fixed order at the end.
+// Partial Gram matrix of the rows this CTA owns.  One CTA per SM, two thread groups (136 threads
+// each own an 8x8 block of the upper triangle); group g takes rows r = g (mod 2) of every staged
+// 16-row chunk, the two groups' sums are combined in a fixed order at the end.
 // part layout: [cta][e = i*8+j][t] (t fastest).
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restrict__ part) {
     extern __shared__ __align__(16) uint8_t gram_smem[];
     // staged rows; every 8-double block is padded to 10 doubles (80 B) so that the 16-byte loads of
     // 8 lanes with consecutive block indices fall into 8 distinct bank groups
-    double (*As)[GRAM_LDS] = reinterpret_cast<double (*)[GRAM_LDS]>(gram_smem);  // [GRAM_ROWS][160]
+    double (*As)[GRAM_LDS] = reinterpret_cast<double (*)[GRAM_LDS]>(gram_smem);
     double* comb = reinterpret_cast<double*>(gram_smem);                  // reused at the end
     const int tid = threadIdx.x;
     const int grp = tid / GRAM_GROUP_THREADS;
@@ -66,9 +87,10 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
     const bool vec_ok = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     constexpr int VEC_PER_CHUNK = GRAM_ROWS * PW / 4;                                   // 512 float4
     constexpr int VEC_PER_THREAD = (VEC_PER_CHUNK + GRAM_THREADS - 1) / GRAM_THREADS;   // 2
-    constexpr int VEC_PER_COL = GRAM_ROWS / 4;                                          // 4
     float4 pre[VEC_PER_THREAD];
 
+    // element idx of a chunk: column = idx % 128 (consecutive lanes -> consecutive smem words),
+    // row quad = idx / 128
     auto prefetch = [&](int chunk) {
         const int r0 = chunk * GRAM_ROWS;
 #pragma unroll
@@ -76,8 +98,8 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
             const int idx = tid + k * GRAM_THREADS;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (idx < VEC_PER_CHUNK) {
-                const int col = idx / VEC_PER_COL;
-                const int r = r0 + ((idx % VEC_PER_COL) << 2);
+                const int col = idx & (PW - 1);
+                const int r = r0 + ((idx >> 7) << 2);
                 const float* src = A + r + (long)col * lda;
                 if (vec_ok && r + 3 < m) {
                     v = *reinterpret_cast<const float4*>(src);
@@ -92,6 +114,10 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
         }
     };
 
+    const double2* pi = reinterpret_cast<const double2*>(&As[0][bi * GRAM_BLK]);
+    const double2* pj = reinterpret_cast<const double2*>(&As[0][bj * GRAM_BLK]);
+    constexpr int ROW_D2 = GRAM_LDS / 2;   // row stride in double2
+
     int chunk = blockIdx.x;
     if (chunk < nchunks) prefetch(chunk);
     for (; chunk < nchunks; chunk += gridDim.x) {
@@ -99,8 +125,8 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
         for (int k = 0; k < VEC_PER_THREAD; ++k) {
             const int idx = tid + k * GRAM_THREADS;
             if (idx < VEC_PER_CHUNK) {
-                const int col = idx / VEC_PER_COL;
-                const int r = (idx % VEC_PER_COL) << 2;
+                const int col = idx & (PW - 1);
+                const int r = (idx >> 7) << 2;
                 const int pc = (col >> 3) * GRAM_BLK + (col & 7);
                 As[r][pc] = (double)pre[k].x;
                 As[r + 1][pc] = (double)pre[k].y;
@@ -111,16 +137,25 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
         __syncthreads();
         if (chunk + (int)gridDim.x < nchunks) prefetch(chunk + gridDim.x);  // in flight during math
         if (t < NTRI) {
-#pragma unroll 2
+            // software-pipelined over this group's rows: operands of row r+2 are loaded while the
+            // 64 DFMAs of row r issue
+            double2 ni[GB / 2], nj[GB / 2];
+#pragma unroll
+            for (int q = 0; q < GB / 2; ++q) { ni[q] = pi[grp * ROW_D2 + q]; nj[q] = pj[grp * ROW_D2 + q]; }
+#pragma unroll
             for (int r = grp; r < GRAM_ROWS; r += GRAM_GROUPS) {
                 double ai[GB], aj[GB];
-                const double2* pi = reinterpret_cast<const double2*>(&As[r][bi * GRAM_BLK]);
-                const double2* pj = reinterpret_cast<const double2*>(&As[r][bj * GRAM_BLK]);
 #pragma unroll
                 for (int q = 0; q < GB / 2; ++q) {
-                    const double2 vi = pi[q], vj = pj[q];
-                    ai[2 * q] = vi.x; ai[2 * q + 1] = vi.y;
-                    aj[2 * q] = vj.x; aj[2 * q + 1] = vj.y;
+                    ai[2 * q] = ni[q].x; ai[2 * q + 1] = ni[q].y;
+                    aj[2 * q] = nj[q].x; aj[2 * q + 1] = nj[q].y;
+                }
+                if (r + GRAM_GROUPS < GRAM_ROWS) {
+#pragma unroll
+                    for (int q = 0; q < GB / 2; ++q) {
+                        ni[q] = pi[(r + GRAM_GROUPS) * ROW_D2 + q];
+                        nj[q] = pj[(r + GRAM_GROUPS) * ROW_D2 + q];
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < GB; ++i)
@@ -150,11 +185,14 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
 
 // G[e] = sum over CTAs of part[c][e], summed in a fixed order: 32 slices of the CTA index per entry,
 // each slice sequential, then the slices in order.  One CTA handles 32 consecutive entries.
+// Also clears the block-row flags of the factor hand-over for this panel.
 __global__ void __launch_bounds__(1024)
-gram128_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ G) {
+gram128_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ G,
+                      int* __restrict__ flags) {
     __shared__ double sh[32][33];
     const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int idx = blockIdx.x * 32 + e;
+    if (blockIdx.x == 0 && threadIdx.x < 4) flags[threadIdx.x] = 0;
     double s = 0.0;
     if (idx < GRAM_ELEMS)
         for (int c = sl; c < nparts; c += 32) s += part[(long)c * GRAM_ELEMS + idx];
@@ -175,23 +213,6 @@ __device__ __forceinline__ double gram_elem(const double* __restrict__ G, int i,
     return G[((j % GB) * GB + (i % GB)) * NTRI + tri_index(bi, bj)];
 }
 
-// Scratch produced for apply128_kernel.
-struct PanelFactors {
-    float Roff[6][32][32];   // off-diagonal 32x32 blocks R(ib, jb), ib < jb, [k][c] row-major
-    float Rdiag[4][32][32];  // diagonal blocks R(b, b), [k][c] row-major; only c >= k is defined
-    float rinv[128];         // 1 / R(c, c)
-};
-__host__ __device__ inline int off_index(int ib, int jb) {  // ib < jb < 4
-    return ib == 0 ? (jb - 1) : (ib == 1 ? (jb + 1) : 5);
-}
-
-// R = chol(G)^T in fp64, one CTA of 256 threads arranged 16 x 16: thread (tx = column residue,
-// ty = row residue) keeps the elements (i, j) = (ty + 16 ia, tx + 16 jb), ia >= jb, of the trailing
-// lower triangle in registers (36 doubles).  Column c is owned by the 16 threads with tx = c % 16 -
-// half a warp - so the pivot is broadcast with a shuffle and each column costs ONE block barrier.
-// Look-ahead: in the step that applies column c-1 every thread updates block column c/16 first, the
-// owner of column c then derives it (pivot, reciprocal square root, scale) while the other warps
-// are still busy with the rest of the rank-1 update.
 __device__ __forceinline__ double rsqrt_f64(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -200,89 +221,128 @@ __device__ __forceinline__ double rsqrt_f64(double x) {
     return fma(0.5 * y, e, y);                 // one Newton step: ~2^-45 relative
 }
 
+// R = chol(G)^T in fp64, one CTA of 256 threads.  Thread (tx = column residue mod 16, ty = row
+// residue mod 16) keeps the elements (i, j) = (ty + 16 ia, tx + 16 jb), ia >= jb, of the trailing
+// lower triangle in registers (36 doubles).  Warp w holds tx in {w, w + 8} (one per half-warp), so
+// consecutive columns belong to different warps and a column's pivot is broadcast by shuffle.
+// Columns travel through a 4-slot shared-memory ring guarded by mbarriers: the owner of column c
+// derives it (pivot, reciprocal square root, scaling) as soon as column c-1 has been applied to ITS
+// entries; nobody waits at a block-wide barrier, the other warps' rank-1 updates run in the shadow
+// of the pivot chain.
+struct CholShared {
+    double col[4][PW];
+    uint64_t full[4];
+    uint64_t empty[4];
+    float rinv[PW];
+};
+
 struct CholOut {
     float* R; long ldr;
     PanelFactors* fac;
     int* info;
 };
 
-// Derives column c (pivot, reciprocal square root, scaling) and publishes it in col[c & 1].
-// Executed by the whole warp that contains the owner half-warp (tx == c % 16).
-template <int CB>
-__device__ __forceinline__ void chol_emit_column(double (&a)[8][8], int c, int tx, int ty,
-                                                 double (*col)[PW], float* rinv_s, const CholOut& o) {
-    const int cr = c & 15;
-    double piv = a[CB][CB];
-    piv = __shfl_sync(0xffffffffu, piv, ((cr & 1) << 4) + cr);   // lane with tx == cr, ty == cr
-    if (tx != cr) return;
-    if (!(piv > 0.0)) {                        // breakdown: numerically rank-deficient panel
-        if (ty == 0) atomicExch(o.info, c + 1);
-        piv = 1e-300;
-    }
-    const double rs = rsqrt_f64(piv);
-#pragma unroll
-    for (int ia = 0; ia < 8; ++ia) {
-        const int i = ty + 16 * ia;
-        double l = 0.0;
-        if (ia >= CB && i >= c) l = (i == c) ? piv * rs : a[ia][CB] * rs;
-        col[c & 1][i] = l;
-    }
-    if (ty == cr) rinv_s[c] = (float)rs;
-}
-
-// Writes column k of L (= row k of R) to the caller's R and to the factor blocks, from col[k & 1].
-// Done by the warps that do NOT own the next column, so it stays off the critical path.
-__device__ __forceinline__ void chol_output_column(int k, int q, const double (*col)[PW],
-                                                   const CholOut& o) {
+// Writes column k of L (= row k of R) to the caller's R and to the factor blocks.
+__device__ __forceinline__ void chol_output_column(int k, int q, const double* colk, const CholOut& o) {
     if (q >= PW) return;
     const int i = q;
     if (i < k) { o.R[k + (long)i * o.ldr] = 0.f; return; }        // strictly lower part of R
-    const float l = (float)col[k & 1][i];
+    const float l = (float)colk[i];
     o.R[k + (long)i * o.ldr] = l;                                  // R(k, i) = L(i, k)
     const int rb = k >> 5, rr = k & 31, ib = i >> 5;
-    if (ib == rb) o.fac->Rdiag[rb][rr][i & 31] = l;
-    else o.fac->Roff[off_index(rb, ib)][rr][i & 31] = l;
+    if (ib == rb) o.fac->Rdiag[rb][rr][perm32(i & 31)] = l;
+    else o.fac->Roff[off_index(rb, ib)][rr][perm32(i & 31)] = l;
 }
 
 template <int CB>
-__device__ __forceinline__ void chol_block_column(double (&a)[8][8], int tx, int ty,
-                                                  double (*col)[PW], float* rinv_s, const CholOut& o) {
-    const int warp = tx >> 1;
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void chol_emit_column(double (&a)[8][8], int c, int tx, int ty, int lane,
+                                                 CholShared& sh, const CholOut& o) {
+    // whole owner warp; the owner half-warp is the one with tx == c % 16
+    const int cr = c & 15;
+    double piv = a[CB][CB];
+    piv = __shfl_sync(0xffffffffu, piv, ((cr >> 3) << 4) | cr);   // lane with tx == cr, ty == cr
+    const int slot = c & 3;
+    if (c >= 4) mbar_wait(smem_u32(&sh.empty[slot]), ((c >> 2) & 1) ^ 1u);   // readers of c-4 done
+    if (tx == cr) {
+        if (!(piv > 0.0)) {                    // breakdown: numerically rank-deficient panel
+            if (ty == 0) atomicExch(o.info, c + 1);
+            piv = 1e-300;
+        }
+        const double rs = rsqrt_f64(piv);
+#pragma unroll
+        for (int ia = 0; ia < 8; ++ia) {
+            const int i = ty + 16 * ia;
+            double l = 0.0;
+            if (ia >= CB && i >= c) l = (i == c) ? piv * rs : a[ia][CB] * rs;
+            sh.col[slot][i] = l;
+        }
+        if (ty == cr) sh.rinv[c] = (float)rs;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&sh.full[slot]));
+}
+
+template <int CB>
+__device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, int tx, int ty,
+                                                  int lane, CholShared& sh, const CholOut& o) {
 #pragma unroll 1
     for (int cr = (CB == 0 ? 1 : 0); cr < 16; ++cr) {
         const int c = CB * 16 + cr, k = c - 1;
-        __syncthreads();                       // column k is in col[k & 1]
+        const int slot = k & 3;
+        mbar_wait(smem_u32(&sh.full[slot]), (k >> 2) & 1u);       // column k has been published
         double ci[8], cj[8];
 #pragma unroll
         for (int q = CB; q < 8; ++q) {
-            ci[q] = col[k & 1][ty + 16 * q];
-            cj[q] = col[k & 1][tx + 16 * q];
+            ci[q] = sh.col[slot][ty + 16 * q];
+            cj[q] = sh.col[slot][tx + 16 * q];
         }
-        // block column CB first (it contains column c) ...
+        // block column CB first (it contains column c) so that its owner can derive column c
 #pragma unroll
         for (int ia = CB; ia < 8; ++ia) a[ia][CB] = fma(-ci[ia], cj[CB], a[ia][CB]);
-        // ... so that its owner can already derive column c
-        const int owner = cr >> 1;
-        if (warp == owner) chol_emit_column<CB>(a, c, tx, ty, col, rinv_s, o);
-        else chol_output_column(k, (((warp - owner - 1) & 7) << 5) + lane, col, o);
+        const int owner = cr & 7;
+        if (warp == owner) {
+            chol_emit_column<CB>(a, c, tx, ty, lane, sh, o);
+        } else {
+            chol_output_column(k, (((warp - owner - 1) & 7) << 5) + lane, sh.col[slot], o);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sh.empty[slot]));    // this warp is done reading column k
         // rest of the rank-1 update
 #pragma unroll
         for (int jb = CB + 1; jb < 8; ++jb)
 #pragma unroll
             for (int ia = jb; ia < 8; ++ia) a[ia][jb] = fma(-ci[ia], cj[jb], a[ia][jb]);
+        if ((c & 31) == 0) {
+            // block-row (c/32 - 1) of R is complete once column c-1 has been written out
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const int b = (c >> 5) - 1;
+                o.fac->rinv[b * 32 + threadIdx.x] = sh.rinv[b * 32 + threadIdx.x];
+                __threadfence();
+                __syncwarp();
+                if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&o.fac->flag[b]) = 1;
+            }
+        }
     }
 }
 
 __global__ void __launch_bounds__(256, 1)
 chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
                PanelFactors* __restrict__ fac, int* __restrict__ info) {
-    __shared__ double col[2][PW];
-    __shared__ float rinv_s[PW];
-    const int tx = threadIdx.x >> 4;   // column residue
-    const int ty = threadIdx.x & 15;   // row residue
+    __shared__ CholShared sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = warp + ((lane >> 4) << 3);   // column residue
+    const int ty = lane & 15;                   // row residue
     const CholOut o{R, ldr, fac, info};
+    // let the dependent apply kernel start right away: it synchronises on fac->flag[], not on
+    // the completion of this grid
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&sh.full[s]), 1); mbar_init(smem_u32(&sh.empty[s]), 8); }
+        fence_barrier_init();
+    }
     double a[8][8];
 #pragma unroll
     for (int ia = 0; ia < 8; ++ia)
@@ -291,91 +351,129 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
             const int i = ty + 16 * ia, j = tx + 16 * jb;
             a[ia][jb] = (ia >= jb && i >= j) ? gram_elem(G, i, j) : 0.0;
         }
-    if ((tx >> 1) == 0) chol_emit_column<0>(a, 0, tx, ty, col, rinv_s, o);   // column 0: no update
-    chol_block_column<0>(a, tx, ty, col, rinv_s, o);
-    chol_block_column<1>(a, tx, ty, col, rinv_s, o);
-    chol_block_column<2>(a, tx, ty, col, rinv_s, o);
-    chol_block_column<3>(a, tx, ty, col, rinv_s, o);
-    chol_block_column<4>(a, tx, ty, col, rinv_s, o);
-    chol_block_column<5>(a, tx, ty, col, rinv_s, o);
-    chol_block_column<6>(a, tx, ty, col, rinv_s, o);
-    chol_block_column<7>(a, tx, ty, col, rinv_s, o);
     __syncthreads();
-    chol_output_column(PW - 1, threadIdx.x, col, o);               // last column
-    if (threadIdx.x < PW) fac->rinv[threadIdx.x] = rinv_s[threadIdx.x];
+    if (warp == 0) chol_emit_column<0>(a, 0, tx, ty, lane, sh, o);   // column 0 needs no update
+    chol_block_column<0>(a, warp, tx, ty, lane, sh, o);
+    chol_block_column<1>(a, warp, tx, ty, lane, sh, o);
+    chol_block_column<2>(a, warp, tx, ty, lane, sh, o);
+    chol_block_column<3>(a, warp, tx, ty, lane, sh, o);
+    chol_block_column<4>(a, warp, tx, ty, lane, sh, o);
+    chol_block_column<5>(a, warp, tx, ty, lane, sh, o);
+    chol_block_column<6>(a, warp, tx, ty, lane, sh, o);
+    chol_block_column<7>(a, warp, tx, ty, lane, sh, o);
+    // last column and last block-row
+    mbar_wait(smem_u32(&sh.full[(PW - 1) & 3]), ((PW - 1) >> 2) & 1u);
+    chol_output_column(PW - 1, threadIdx.x, sh.col[(PW - 1) & 3], o);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        fac->rinv[96 + threadIdx.x] = sh.rinv[96 + threadIdx.x];
+        __threadfence();
+        __syncwarp();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&fac->flag[3]) = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int APPLY_ROWS = 64;   // rows (= threads) per CTA
+// Q = A R^-1, 64 rows per CTA, four threads per row: thread (r, p) owns the columns c = p (mod 4)
+// of the current 32-column block (8 accumulators).  Per block jb: wait for block-row jb of R,
+// project out the earlier blocks (a_jb -= q_ib R(ib, jb)), then forward substitution against the
+// diagonal block, the owner of column k broadcasting q_k to the other three threads of its row.
+constexpr int APPLY_ROWS = 64;
+constexpr int APPLY_THREADS = 4 * APPLY_ROWS;
 struct ApplySmem {
-    float Q[PW][APPLY_ROWS];   // staged row block, column-major (conflict-free per-lane access)
-    PanelFactors fac;
+    float Q[PW][APPLY_ROWS];   // staged row block, column-major
+    float Rb[4][32][32];       // R(0..jb, jb) blocks of the current stage ([3] = diagonal block)
+    float rinv[32];
 };
 
-__global__ void __launch_bounds__(APPLY_ROWS)
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(APPLY_THREADS)
 apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __restrict__ fac,
                 __half* __restrict__ Qh, long ldqh) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     ApplySmem& s = *reinterpret_cast<ApplySmem*>(smem_raw);
-    const int t = threadIdx.x;
-    const int row = blockIdx.x * APPLY_ROWS + t;
-    const bool ok = row < m;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * APPLY_ROWS;
+    const int r = tid >> 2, p = tid & 3;     // compute mapping: row inside the block, column part
+    const int lane = tid & 31;
 
-    {   // factors -> smem (float4 copies)
-        const float4* src = reinterpret_cast<const float4*>(fac);
-        float4* dst = reinterpret_cast<float4*>(&s.fac);
-        for (int i = t; i < (int)(sizeof(PanelFactors) / 16); i += APPLY_ROWS) dst[i] = src[i];
+    // stage the row block (coalesced: a warp reads 32 consecutive rows of one column)
+    {
+        const int sr = tid & (APPLY_ROWS - 1), sc0 = tid >> 6;      // 4 columns per pass
+        const bool ok = row0 + sr < m;
+#pragma unroll 8
+        for (int c = sc0; c < PW; c += 4) s.Q[c][sr] = ok ? A[row0 + sr + (long)c * lda] : 0.f;
     }
-#pragma unroll 32
-    for (int c = 0; c < PW; ++c) s.Q[c][t] = ok ? A[row + (long)c * lda] : 0.f;   // 32 loads in flight
-    __syncthreads();
 
 #pragma unroll 1
     for (int jb = 0; jb < 4; ++jb) {
-        float acc[32];
+        // wait until the Cholesky kernel has published block-row jb of R
+        if (tid == 0) {
+            while (ld_acquire(&fac->flag[jb]) == 0) { __nanosleep(64); }
+        }
+        __syncthreads();   // also orders the previous stage's Q writes and Rb reads
+        // R(ib, jb) for ib < jb, the diagonal block and 1/diag -> smem (L1-bypassing loads)
+        for (int e = tid; e < (jb + 1) * 256; e += APPLY_THREADS) {
+            const int b = e >> 8, w4 = e & 255;           // block, float4 index inside it
+            const float4* src = reinterpret_cast<const float4*>(
+                b < jb ? &fac->Roff[off_index(b, jb)][0][0] : &fac->Rdiag[jb][0][0]);
+            reinterpret_cast<float4*>(&s.Rb[b < jb ? b : 3][0][0])[w4] = __ldcg(src + w4);
+        }
+        if (tid < 32) s.rinv[tid] = __ldcg(&fac->rinv[jb * 32 + tid]);
+        __syncthreads();
+
+        float acc[8];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = s.Q[jb * 32 + c][t];
-        // project out the finished blocks: a_jb -= q_ib * R(ib, jb)
+        for (int q = 0; q < 8; ++q) acc[q] = s.Q[jb * 32 + 4 * q + p][r];
+        // project out the finished blocks
 #pragma unroll 1
         for (int ib = 0; ib < jb; ++ib) {
-            const float (*Rb)[32] = s.fac.Roff[off_index(ib, jb)];
 #pragma unroll 8
             for (int k = 0; k < 32; ++k) {
-                const float qk = s.Q[ib * 32 + k][t];
-                const float4* rr = reinterpret_cast<const float4*>(Rb[k]);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 r4 = rr[q];
-                    acc[4 * q] = fmaf(-qk, r4.x, acc[4 * q]);
-                    acc[4 * q + 1] = fmaf(-qk, r4.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(-qk, r4.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(-qk, r4.w, acc[4 * q + 3]);
-                }
+                const float qk = s.Q[ib * 32 + k][r];
+                const float4 r0 = *reinterpret_cast<const float4*>(&s.Rb[ib][k][p * 8]);
+                const float4 r1 = *reinterpret_cast<const float4*>(&s.Rb[ib][k][p * 8 + 4]);
+                acc[0] = fmaf(-qk, r0.x, acc[0]); acc[1] = fmaf(-qk, r0.y, acc[1]);
+                acc[2] = fmaf(-qk, r0.z, acc[2]); acc[3] = fmaf(-qk, r0.w, acc[3]);
+                acc[4] = fmaf(-qk, r1.x, acc[4]); acc[5] = fmaf(-qk, r1.y, acc[5]);
+                acc[6] = fmaf(-qk, r1.z, acc[6]); acc[7] = fmaf(-qk, r1.w, acc[7]);
             }
         }
-        // normalise against the diagonal block by forward substitution:
-        // q_k = a_k / R(k,k); a_c -= q_k R(k,c) for c > k
-        const float (*Rd)[32] = s.fac.Rdiag[jb];
-        float qv[32];
+        // forward substitution against the diagonal block; column k = 4*kq + kp is owned by part kp
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            const float qk = acc[k] * s.fac.rinv[jb * 32 + k];
-            qv[k] = qk;
+            const int kq = k >> 2, kp = k & 3;
+            float qk = acc[kq] * s.rinv[k];
+            qk = __shfl_sync(0xffffffffu, qk, (lane & ~3) | kp);
+            if (p == kp) acc[kq] = qk;
+            const float4 r0 = *reinterpret_cast<const float4*>(&s.Rb[3][k][p * 8]);
+            const float4 r1 = *reinterpret_cast<const float4*>(&s.Rb[3][k][p * 8 + 4]);
+            const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-            for (int q = (k + 1) / 4; q < 8; ++q) {
-                const float4 r4 = reinterpret_cast<const float4*>(Rd[k])[q];
-                if (4 * q > k) acc[4 * q] = fmaf(-qk, r4.x, acc[4 * q]);
-                if (4 * q + 1 > k) acc[4 * q + 1] = fmaf(-qk, r4.y, acc[4 * q + 1]);
-                if (4 * q + 2 > k) acc[4 * q + 2] = fmaf(-qk, r4.z, acc[4 * q + 2]);
-                if (4 * q + 3 > k) acc[4 * q + 3] = fmaf(-qk, r4.w, acc[4 * q + 3]);
+            for (int q = kq; q < 8; ++q) {
+                // column 4q + p is updated iff it lies to the right of column k
+                if (q > kq || p > kp) acc[q] = fmaf(-qk, rr[q], acc[q]);
             }
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            s.Q[jb * 32 + c][t] = qv[c];
-            if (ok) {
-                A[row + (long)(jb * 32 + c) * lda] = qv[c];
-                if (Qh) Qh[row + (long)(jb * 32 + c) * ldqh] = __float2half_rn(qv[c]);
+        for (int q = 0; q < 8; ++q) s.Q[jb * 32 + 4 * q + p][r] = acc[q];
+        __syncthreads();
+        // write block jb out (coalesced), fp32 in place and the fp16 shadow
+        {
+            const int sr = tid & (APPLY_ROWS - 1), sc0 = tid >> 6;
+            if (row0 + sr < m) {
+#pragma unroll
+                for (int c = sc0; c < 32; c += 4) {
+                    const float v = s.Q[jb * 32 + c][sr];
+                    A[row0 + sr + (long)(jb * 32 + c) * lda] = v;
+                    if (Qh) Qh[row0 + sr + (long)(jb * 32 + c) * ldqh] = __float2half_rn(v);
+                }
             }
         }
     }
@@ -402,11 +500,11 @@ ScratchLayout scratch_layout(int m, int num_sms) {
     return L;
 }
 
+constexpr int GRAM_SMEM = GRAM_ELEMS * (int)sizeof(double);   // combine buffer (> 16x160 staging tile)
+
 }  // namespace
 
 size_t panel_scratch_bytes(int m, int num_sms) { return scratch_layout(m, num_sms).total; }
-
-constexpr int GRAM_SMEM = GRAM_ELEMS * (int)sizeof(double);   // combine buffer (> 16x160 staging tile)
 
 cudaError_t panel_init() {
     cudaError_t e = cudaFuncSetAttribute(gram128_f64_kernel,
@@ -426,11 +524,27 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
     int* info = reinterpret_cast<int*>(base + L.info_off);
     const int ggrid = gram_grid(m, num_sms);
 
+    cudaError_t le;
     gram128_f64_kernel<<<ggrid, GRAM_THREADS, GRAM_SMEM, stream>>>(A, lda, m, part);
-    gram128_reduce_kernel<<<(GRAM_ELEMS + 31) / 32, 1024, 0, stream>>>(part, ggrid, G);
+    if ((le = cudaGetLastError()) != cudaSuccess) { fprintf(stderr, "later_b200: gram128 launch: %s\n", cudaGetErrorString(le)); return le; }
+    gram128_reduce_kernel<<<(GRAM_ELEMS + 31) / 32, 1024, 0, stream>>>(part, ggrid, G, fac->flag);
+    if ((le = cudaGetLastError()) != cudaSuccess) { fprintf(stderr, "later_b200: gram reduce launch: %s\n", cudaGetErrorString(le)); return le; }
     chol128_kernel<<<1, 256, 0, stream>>>(G, R, ldr, fac, info);
-    apply128_kernel<<<(m + APPLY_ROWS - 1) / APPLY_ROWS, APPLY_ROWS, sizeof(ApplySmem), stream>>>(
-        A, lda, m, fac, Qh, ldqh);
+    if ((le = cudaGetLastError()) != cudaSuccess) { fprintf(stderr, "later_b200: chol128 launch: %s\n", cudaGetErrorString(le)); return le; }
+    // programmatic dependent launch: the apply grid may start while the Cholesky grid is running
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((m + APPLY_ROWS - 1) / APPLY_ROWS);
+    cfg.blockDim = dim3(APPLY_THREADS);
+    cfg.dynamicSmemBytes = sizeof(ApplySmem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const PanelFactors* cfac = fac;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, apply128_kernel, A, lda, m, cfac, Qh, ldqh);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

@@ -475,7 +475,8 @@ int later_b200_gemm_update(later_b200_ctx* ctx, const void* Qh, int q_rows, int 
         (e = make_tensor_map_f16(&bmap, bm, 64, bn)) != cudaSuccess)
         return cuda_fail(ctx, e, "tensor map encode");
     const bool tma_ok = ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
-                        (subtract == 0 || (Ch && ldch % 8 == 0 && (reinterpret_cast<uintptr_t>(Ch) & 15) == 0)) &&
+                        (subtract == 0 ? Ch == nullptr
+                                       : (Ch && ldch % 8 == 0 && (reinterpret_cast<uintptr_t>(Ch) & 15) == 0)) &&
                         Nc % bn == 0;
     if (tma_ok)
         e = tc_update_tma(ctx->stream, ctx->num_sms, q64, bmap, bn, 0, q_rows, colA, K, 0, Nc, C, q_rows,
