@@ -382,7 +382,7 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
 constexpr int APPLY_ROWS = 64;
 constexpr int APPLY_THREADS = 4 * APPLY_ROWS;
 struct ApplySmem {
-    float Q[PW][APPLY_ROWS];   // staged row block, column-major
+    float Q[PW][APPLY_ROWS + 1];   // staged row block, column-major (+1: parts p=0..3 hit 4 banks)
     float Rb[4][32][32];       // R(0..jb, jb) blocks of the current stage ([3] = diagonal block)
     float rinv[32];
 };
@@ -431,34 +431,63 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
         float acc[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] = s.Q[jb * 32 + 4 * q + p][r];
-        // project out the finished blocks
+        // project out the finished blocks: a_jb -= q_ib R(ib, jb), software-pipelined over groups
+        // of 8 k-steps (the operands of group it+1 are loaded before the 64 FMAs of group it)
+        {
+            const int T = jb * 4;                     // groups of 8 consecutive k over all ib < jb
+            float qn[8];
+            float4 ran[8], rbn[8];
+            auto load_group = [&](int it) {
+                const int ib = it >> 2, k0 = (it & 3) << 3;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    qn[u] = s.Q[ib * 32 + k0 + u][r];
+                    ran[u] = *reinterpret_cast<const float4*>(&s.Rb[ib][k0 + u][p * 8]);
+                    rbn[u] = *reinterpret_cast<const float4*>(&s.Rb[ib][k0 + u][p * 8 + 4]);
+                }
+            };
+            if (T > 0) load_group(0);
 #pragma unroll 1
-        for (int ib = 0; ib < jb; ++ib) {
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                const float qk = s.Q[ib * 32 + k][r];
-                const float4 r0 = *reinterpret_cast<const float4*>(&s.Rb[ib][k][p * 8]);
-                const float4 r1 = *reinterpret_cast<const float4*>(&s.Rb[ib][k][p * 8 + 4]);
-                acc[0] = fmaf(-qk, r0.x, acc[0]); acc[1] = fmaf(-qk, r0.y, acc[1]);
-                acc[2] = fmaf(-qk, r0.z, acc[2]); acc[3] = fmaf(-qk, r0.w, acc[3]);
-                acc[4] = fmaf(-qk, r1.x, acc[4]); acc[5] = fmaf(-qk, r1.y, acc[5]);
-                acc[6] = fmaf(-qk, r1.z, acc[6]); acc[7] = fmaf(-qk, r1.w, acc[7]);
+            for (int it = 0; it < T; ++it) {
+                float qv[8];
+                float4 ra[8], rb[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { qv[u] = qn[u]; ra[u] = ran[u]; rb[u] = rbn[u]; }
+                if (it + 1 < T) load_group(it + 1);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    acc[0] = fmaf(-qv[u], ra[u].x, acc[0]); acc[1] = fmaf(-qv[u], ra[u].y, acc[1]);
+                    acc[2] = fmaf(-qv[u], ra[u].z, acc[2]); acc[3] = fmaf(-qv[u], ra[u].w, acc[3]);
+                    acc[4] = fmaf(-qv[u], rb[u].x, acc[4]); acc[5] = fmaf(-qv[u], rb[u].y, acc[5]);
+                    acc[6] = fmaf(-qv[u], rb[u].z, acc[6]); acc[7] = fmaf(-qv[u], rb[u].w, acc[7]);
+                }
             }
         }
-        // forward substitution against the diagonal block; column k = 4*kq + kp is owned by part kp
+        // forward substitution against the diagonal block; column k = 4*kq + kp is owned by part kp.
+        // The rows of the diagonal block needed by 4 consecutive k are loaded ahead of the
+        // dependent multiply / shuffle / FMA chain.
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const int kq = k >> 2, kp = k & 3;
-            float qk = acc[kq] * s.rinv[k];
-            qk = __shfl_sync(0xffffffffu, qk, (lane & ~3) | kp);
-            if (p == kp) acc[kq] = qk;
-            const float4 r0 = *reinterpret_cast<const float4*>(&s.Rb[3][k][p * 8]);
-            const float4 r1 = *reinterpret_cast<const float4*>(&s.Rb[3][k][p * 8 + 4]);
-            const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        for (int kq = 0; kq < 8; ++kq) {
+            float4 da[4], db[4];
+            float rv[4];
 #pragma unroll
-            for (int q = kq; q < 8; ++q) {
-                // column 4q + p is updated iff it lies to the right of column k
-                if (q > kq || p > kp) acc[q] = fmaf(-qk, rr[q], acc[q]);
+            for (int kp = 0; kp < 4; ++kp) {
+                da[kp] = *reinterpret_cast<const float4*>(&s.Rb[3][4 * kq + kp][p * 8]);
+                db[kp] = *reinterpret_cast<const float4*>(&s.Rb[3][4 * kq + kp][p * 8 + 4]);
+                rv[kp] = s.rinv[4 * kq + kp];
+            }
+#pragma unroll
+            for (int kp = 0; kp < 4; ++kp) {
+                float qk = acc[kq] * rv[kp];
+                qk = __shfl_sync(0xffffffffu, qk, (lane & ~3) | kp);
+                if (p == kp) acc[kq] = qk;
+                const float rr[8] = {da[kp].x, da[kp].y, da[kp].z, da[kp].w,
+                                     db[kp].x, db[kp].y, db[kp].z, db[kp].w};
+#pragma unroll
+                for (int q = kq; q < 8; ++q) {
+                    // column 4q + p is updated iff it lies to the right of column k = 4 kq + kp
+                    if (q > kq || p > kp) acc[q] = fmaf(-qk, rr[q], acc[q]);
+                }
             }
         }
 #pragma unroll

@@ -1,0 +1,62 @@
+"""torchrun worker: row-sharded TSQR on real GPUs (NCCL), checked against the single-GPU result.
+Usage: torchrun --nproc-per-node P tests/helpers/tsqr_worker.py m n"""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from later_b200 import qr  # noqa: E402
+from later_b200.tsqr import tsqr_rgsqrf  # noqa: E402
+
+
+def main():
+    m, n = int(sys.argv[1]), int(sys.argv[2])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(1234)          # same global matrix on every rank
+    A_glob = torch.randn(m, n, device="cuda", generator=g)
+    mloc = m // world
+    A0 = A_glob[rank * mloc:(rank + 1) * mloc].clone()
+    A = qr.to_colmajor(A0)
+    R = qr.colmajor_empty(n, n)
+    tsqr_rgsqrf(mloc, n, A, mloc, R, n)
+    torch.cuda.synchronize()
+    # every rank must hold the same R, bit for bit
+    Rs = [torch.empty_like(R.contiguous()) for _ in range(world)]
+    dist.all_gather(Rs, R.contiguous())
+    same = all(torch.equal(Rs[0], x) for x in Rs)
+    # global checks: ||A - Q R|| and ||I - Q^T Q|| assembled with all-reduces of small quantities
+    res2 = torch.linalg.norm((A0 - A @ R).double()) ** 2
+    nrm2 = torch.linalg.norm(A0.double()) ** 2
+    G = (A.t() @ A).double()
+    dist.all_reduce(res2); dist.all_reduce(nrm2); dist.all_reduce(G)
+    back = float(torch.sqrt(res2 / nrm2))
+    G.diagonal().sub_(1.0)
+    orth = float(torch.linalg.norm(G) / n)
+    ok = same and back < 5e-4 and orth < 5e-5 and bool((R.diagonal() > 0).all()) \
+        and float(torch.tril(R, -1).abs().max()) == 0.0
+    if rank == 0:
+        # against the single-GPU factorisation of the whole matrix
+        c = qr.Context()
+        A1 = qr.to_colmajor(A_glob)
+        R1 = qr.colmajor_empty(n, n)
+        qr.later_rgsqrf(c, m, n, A1, m, R1, n)
+        rdiff = float((R - R1).abs().max() / R1.abs().max())
+        ok = ok and rdiff < 5e-3
+        print(f"TSQR world={world} {m}x{n}: same_R={same} backward={back:.3e} orth/n={orth:.3e} "
+              f"|R-R1|/|R1|={rdiff:.3e} {'OK' if ok else 'FAIL'}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
