@@ -1,6 +1,7 @@
 // 128-column tall-skinny panel QR (see panel.cuh).  Four kernels per panel:
 //   gram128_f64_kernel    one pass over the panel: all column norms and dot products, exact
-//                         fp32 x fp32 products accumulated in fp64, per-CTA partial Gram blocks
+//                         fp32 x fp32 products accumulated in fp64 on the fp64 tensor path
+//                         (mma.sync.m8n8k4.f64), per-CTA partial Gram blocks
 //   gram128_reduce_kernel fixed-order sum of the per-CTA partials (deterministic)
 //   chol128_kernel        R = chol(G) in fp64 on one CTA: trailing matrix in registers, columns
 //                         broadcast through an mbarrier-guarded shared-memory ring (no block-wide
@@ -22,26 +23,24 @@ namespace {
 using namespace ptx;
 
 constexpr int PW = kPanelWidth;        // 128
-constexpr int GB = 8;                  // Gram register block (GB x GB doubles per thread)
-constexpr int NBLK = PW / GB;          // 16 blocks per dimension
-constexpr int NTRI = NBLK * (NBLK + 1) / 2;  // 136 upper-triangular blocks
-constexpr int GRAM_GROUP_THREADS = 144;  // 136 of them own a block
-constexpr int GRAM_GROUPS = 2;
-constexpr int GRAM_THREADS = GRAM_GROUP_THREADS * GRAM_GROUPS;   // 288
-constexpr int GRAM_ROWS = 16;          // rows staged per chunk
-constexpr int GRAM_BLK = 10;           // smem doubles per 8-column block (8 + 2 pad)
-constexpr int GRAM_LDS = NBLK * GRAM_BLK;   // 160 doubles per staged row
-constexpr int GRAM_ELEMS = NTRI * GB * GB;  // 8704 doubles per partial
+constexpr int GW = 32;                 // Gram block owned by one warp: GW x GW (4 x 4 DMMA tiles)
+constexpr int NGB = PW / GW;           // 4 blocks per dimension
+constexpr int NTRI = NGB * (NGB + 1) / 2;    // 10 upper-triangular blocks = 10 warps
+constexpr int GRAM_THREADS = NTRI * 32;      // 320
+constexpr int GRAM_ROWS = 16;          // rows staged per chunk (4 DMMA k-steps)
+constexpr int GRAM_LDS = PW + 4;       // 132 doubles per staged row: the 4 rows of a k-step land in
+                                       // 4 different bank groups (row stride = 32 B mod 128 B)
+constexpr int GRAM_ELEMS = NTRI * GW * GW;   // 10240 doubles per partial: [block][i][j]
 
 // Upper-triangular block index t -> (bi, bj), bi <= bj, row-major enumeration.
 __host__ __device__ inline void tri_coords(int t, int& bi, int& bj) {
     int b = 0, rem = t;
-    while (rem >= NBLK - b) { rem -= NBLK - b; ++b; }
+    while (rem >= NGB - b) { rem -= NGB - b; ++b; }
     bi = b;
     bj = b + rem;
 }
 __host__ __device__ inline int tri_index(int bi, int bj) {  // bi <= bj
-    return bi * NBLK - bi * (bi - 1) / 2 + (bj - bi);
+    return bi * NGB - bi * (bi - 1) / 2 + (bj - bi);
 }
 
 // Factors handed from the Cholesky kernel to the apply kernel.  Columns inside a 32-wide block are
@@ -60,28 +59,31 @@ __host__ __device__ inline int off_index(int ib, int jb) {  // ib < jb < 4
 __host__ __device__ inline int perm32(int c) { return ((c & 3) << 3) | (c >> 2); }
 
 // ---------------------------------------------------------------------------------------------
-// Partial Gram matrix of the rows this CTA owns.  One CTA per SM, two thread groups (136 threads
-// each own an 8x8 block of the upper triangle); group g takes rows r = g (mod 2) of every staged
-// 16-row chunk, the two groups' sums are combined in a fixed order at the end.
-// part layout: [cta][e = i*8+j][t] (t fastest).
+// Partial Gram matrix of the rows this CTA owns, on the fp64 tensor path: warp w owns the 32 x 32
+// block (bi, bj), bi <= bj, of G as 4 x 4 accumulator tiles of mma.sync.m8n8k4.f64 (DMMA runs at the
+// DFMA rate on B200, 64 FMA/clk/SM measured, but needs 4x fewer shared-memory wavefronts and 16x
+// fewer issue slots than an 8x8 register-blocked DFMA loop).  Products of fp32 inputs are exact in
+// fp64.  part layout: [cta][block][i][j].
+__device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restrict__ part) {
-    extern __shared__ __align__(16) uint8_t gram_smem[];
-    // staged rows; every 8-double block is padded to 10 doubles (80 B) so that the 16-byte loads of
-    // 8 lanes with consecutive block indices fall into 8 distinct bank groups
-    double (*As)[GRAM_LDS] = reinterpret_cast<double (*)[GRAM_LDS]>(gram_smem);
-    double* comb = reinterpret_cast<double*>(gram_smem);                  // reused at the end
+    __shared__ __align__(16) double As[GRAM_ROWS][GRAM_LDS];   // 16.5 KiB
     const int tid = threadIdx.x;
-    const int grp = tid / GRAM_GROUP_THREADS;
-    const int t = tid - grp * GRAM_GROUP_THREADS;
-    int bi = 0, bj = 0;
-    if (t < NTRI) tri_coords(t, bi, bj);
+    const int warp = tid >> 5, lane = tid & 31;
+    int bi, bj;
+    tri_coords(warp, bi, bj);
+    const int fr = lane & 3;       // row of the k-step this lane feeds (fragment K index)
+    const int fc = lane >> 2;      // column inside an 8-wide tile (fragment M / N index)
 
-    double acc[GB][GB];
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < GB; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < GB; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     const int nchunks = (m + GRAM_ROWS - 1) / GRAM_ROWS;
     const bool vec_ok = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
@@ -114,10 +116,6 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
         }
     };
 
-    const double2* pi = reinterpret_cast<const double2*>(&As[0][bi * GRAM_BLK]);
-    const double2* pj = reinterpret_cast<const double2*>(&As[0][bj * GRAM_BLK]);
-    constexpr int ROW_D2 = GRAM_LDS / 2;   // row stride in double2
-
     int chunk = blockIdx.x;
     if (chunk < nchunks) prefetch(chunk);
     for (; chunk < nchunks; chunk += gridDim.x) {
@@ -127,60 +125,41 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
             if (idx < VEC_PER_CHUNK) {
                 const int col = idx & (PW - 1);
                 const int r = (idx >> 7) << 2;
-                const int pc = (col >> 3) * GRAM_BLK + (col & 7);
-                As[r][pc] = (double)pre[k].x;
-                As[r + 1][pc] = (double)pre[k].y;
-                As[r + 2][pc] = (double)pre[k].z;
-                As[r + 3][pc] = (double)pre[k].w;
+                As[r][col] = (double)pre[k].x;
+                As[r + 1][col] = (double)pre[k].y;
+                As[r + 2][col] = (double)pre[k].z;
+                As[r + 3][col] = (double)pre[k].w;
             }
         }
         __syncthreads();
         if (chunk + (int)gridDim.x < nchunks) prefetch(chunk + gridDim.x);  // in flight during math
-        if (t < NTRI) {
-            // software-pipelined over this group's rows: operands of row r+2 are loaded while the
-            // 64 DFMAs of row r issue
-            double2 ni[GB / 2], nj[GB / 2];
 #pragma unroll
-            for (int q = 0; q < GB / 2; ++q) { ni[q] = pi[grp * ROW_D2 + q]; nj[q] = pj[grp * ROW_D2 + q]; }
+        for (int ks = 0; ks < GRAM_ROWS / 4; ++ks) {
+            double a[4], b[4];
 #pragma unroll
-            for (int r = grp; r < GRAM_ROWS; r += GRAM_GROUPS) {
-                double ai[GB], aj[GB];
+            for (int t = 0; t < 4; ++t) a[t] = As[ks * 4 + fr][bi * GW + t * 8 + fc];
+            if (bi == bj) {
 #pragma unroll
-                for (int q = 0; q < GB / 2; ++q) {
-                    ai[2 * q] = ni[q].x; ai[2 * q + 1] = ni[q].y;
-                    aj[2 * q] = nj[q].x; aj[2 * q + 1] = nj[q].y;
-                }
-                if (r + GRAM_GROUPS < GRAM_ROWS) {
+                for (int t = 0; t < 4; ++t) b[t] = a[t];
+            } else {
 #pragma unroll
-                    for (int q = 0; q < GB / 2; ++q) {
-                        ni[q] = pi[(r + GRAM_GROUPS) * ROW_D2 + q];
-                        nj[q] = pj[(r + GRAM_GROUPS) * ROW_D2 + q];
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < GB; ++i)
-#pragma unroll
-                    for (int j = 0; j < GB; ++j) acc[i][j] = fma(ai[i], aj[j], acc[i][j]);
+                for (int t = 0; t < 4; ++t) b[t] = As[ks * 4 + fr][bj * GW + t * 8 + fc];
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_884(acc[i][j], a[i], b[j]);
         }
         __syncthreads();
     }
-    // combine the groups (group 0 + group 1, fixed order) and emit the CTA's partial
-    if (grp == 1 && t < NTRI) {
+    // accumulator tile (i, j): lane holds G[8 i + lane / 4][8 j + 2 (lane % 4) + {0, 1}] of the block
+    double* dst = part + (long)blockIdx.x * GRAM_ELEMS + (long)warp * GW * GW;
 #pragma unroll
-        for (int i = 0; i < GB; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < GB; ++j) comb[(i * GB + j) * NTRI + t] = acc[i][j];
-    }
-    __syncthreads();
-    if (grp == 0 && t < NTRI) {
-        double* dst = part + (long)blockIdx.x * GRAM_ELEMS + t;
-#pragma unroll
-        for (int i = 0; i < GB; ++i)
-#pragma unroll
-            for (int j = 0; j < GB; ++j)
-                dst[(i * GB + j) * NTRI] = acc[i][j] + comb[(i * GB + j) * NTRI + t];
-    }
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2*>(&dst[(8 * i + fc) * GW + 8 * j + 2 * fr]) =
+                make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
 // G[e] = sum over CTAs of part[c][e], summed in a fixed order: 32 slices of the CTA index per entry,
@@ -207,10 +186,10 @@ gram128_reduce_kernel(const double* __restrict__ part, int nparts, double* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// Element (i, j), i >= j, of the symmetric Gram matrix stored as packed upper blocks.
+// Element (i, j), i >= j, of the symmetric Gram matrix stored as upper 32 x 32 blocks [block][r][c].
 __device__ __forceinline__ double gram_elem(const double* __restrict__ G, int i, int j) {
-    const int bi = j / GB, bj = i / GB;  // upper block (row block of j, column block of i)
-    return G[((j % GB) * GB + (i % GB)) * NTRI + tri_index(bi, bj)];
+    const int bi = j / GW, bj = i / GW;  // upper block: row block of j, column block of i
+    return G[tri_index(bi, bj) * GW * GW + (j % GW) * GW + (i % GW)];
 }
 
 __device__ __forceinline__ double rsqrt_f64(double x) {
@@ -375,15 +354,18 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Q = A R^-1, 64 rows per CTA, four threads per row: thread (r, p) owns the columns c = p (mod 4)
-// of the current 32-column block (8 accumulators).  Per block jb: wait for block-row jb of R,
-// project out the earlier blocks (a_jb -= q_ib R(ib, jb)), then forward substitution against the
-// diagonal block, the owner of column k broadcasting q_k to the other three threads of its row.
-constexpr int APPLY_ROWS = 64;
-constexpr int APPLY_THREADS = 4 * APPLY_ROWS;
+// Q = A R^-1.  128 rows per CTA, 128 threads: thread (rg, p) owns a 4-row x 8-column register tile -
+// rows 4 rg .. 4 rg + 3 and the columns c = p (mod 4) of the current 32-column block - so every
+// shared-memory operand it loads (4 q values, 8 R values, both as 16-byte loads) feeds 32 FMAs.
+// Per block jb: wait for block-row jb of R (flag raised by the Cholesky kernel, which is still
+// running), project out the earlier blocks (a_jb -= q_ib R(ib, jb)), then forward substitution
+// against the diagonal block, the owner of column k broadcasting q_k to the three other parts.
+constexpr int APPLY_ROWS = 128;
+constexpr int APPLY_THREADS = APPLY_ROWS;        // (APPLY_ROWS / 4) row groups x 4 column parts
+constexpr int APPLY_LDQ = APPLY_ROWS + 8;        // 136 floats: parts p = 0..3 land 8 banks apart
 struct ApplySmem {
-    float Q[PW][APPLY_ROWS + 1];   // staged row block, column-major (+1: parts p=0..3 hit 4 banks)
-    float Rb[4][32][32];       // R(0..jb, jb) blocks of the current stage ([3] = diagonal block)
+    float Q[PW][APPLY_LDQ];    // staged row block, column-major
+    float Rb[4][32][32];       // R(0..jb-1, jb) blocks of the current stage, [3] = diagonal block
     float rinv[32];
 };
 
@@ -400,16 +382,13 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
     ApplySmem& s = *reinterpret_cast<ApplySmem*>(smem_raw);
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * APPLY_ROWS;
-    const int r = tid >> 2, p = tid & 3;     // compute mapping: row inside the block, column part
+    const int rg = tid >> 2, p = tid & 3;    // row group (rows 4 rg ..), column part
     const int lane = tid & 31;
+    const bool row_ok = row0 + tid < m;      // staging / write-out mapping: thread = row
 
     // stage the row block (coalesced: a warp reads 32 consecutive rows of one column)
-    {
-        const int sr = tid & (APPLY_ROWS - 1), sc0 = tid >> 6;      // 4 columns per pass
-        const bool ok = row0 + sr < m;
-#pragma unroll 8
-        for (int c = sc0; c < PW; c += 4) s.Q[c][sr] = ok ? A[row0 + sr + (long)c * lda] : 0.f;
-    }
+#pragma unroll 16
+    for (int c = 0; c < PW; ++c) s.Q[c][tid] = row_ok ? A[row0 + tid + (long)c * lda] : 0.f;
 
 #pragma unroll 1
     for (int jb = 0; jb < 4; ++jb) {
@@ -418,7 +397,6 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
             while (ld_acquire(&fac->flag[jb]) == 0) { __nanosleep(64); }
         }
         __syncthreads();   // also orders the previous stage's Q writes and Rb reads
-        // R(ib, jb) for ib < jb, the diagonal block and 1/diag -> smem (L1-bypassing loads)
         for (int e = tid; e < (jb + 1) * 256; e += APPLY_THREADS) {
             const int b = e >> 8, w4 = e & 255;           // block, float4 index inside it
             const float4* src = reinterpret_cast<const float4*>(
@@ -428,20 +406,21 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
         if (tid < 32) s.rinv[tid] = __ldcg(&fac->rinv[jb * 32 + tid]);
         __syncthreads();
 
-        float acc[8];
+        float acc[4][8];                         // [row][q]: column 4 q + p of block jb
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = s.Q[jb * 32 + 4 * q + p][r];
-        // project out the finished blocks: a_jb -= q_ib R(ib, jb), software-pipelined over groups
-        // of 8 k-steps (the operands of group it+1 are loaded before the 64 FMAs of group it)
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(&s.Q[jb * 32 + 4 * q + p][4 * rg]);
+            acc[0][q] = v.x; acc[1][q] = v.y; acc[2][q] = v.z; acc[3][q] = v.w;
+        }
+        // project out the finished blocks, software-pipelined over groups of 4 k-steps
         {
-            const int T = jb * 4;                     // groups of 8 consecutive k over all ib < jb
-            float qn[8];
-            float4 ran[8], rbn[8];
+            const int T = jb * 8;                // groups of 4 consecutive k over all ib < jb
+            float4 qn[4], ran[4], rbn[4];
             auto load_group = [&](int it) {
-                const int ib = it >> 2, k0 = (it & 3) << 3;
+                const int ib = it >> 3, k0 = (it & 7) << 2;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    qn[u] = s.Q[ib * 32 + k0 + u][r];
+                for (int u = 0; u < 4; ++u) {
+                    qn[u] = *reinterpret_cast<const float4*>(&s.Q[ib * 32 + k0 + u][4 * rg]);
                     ran[u] = *reinterpret_cast<const float4*>(&s.Rb[ib][k0 + u][p * 8]);
                     rbn[u] = *reinterpret_cast<const float4*>(&s.Rb[ib][k0 + u][p * 8 + 4]);
                 }
@@ -449,23 +428,23 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
             if (T > 0) load_group(0);
 #pragma unroll 1
             for (int it = 0; it < T; ++it) {
-                float qv[8];
-                float4 ra[8], rb[8];
+                float4 qv[4], ra[4], rb[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { qv[u] = qn[u]; ra[u] = ran[u]; rb[u] = rbn[u]; }
+                for (int u = 0; u < 4; ++u) { qv[u] = qn[u]; ra[u] = ran[u]; rb[u] = rbn[u]; }
                 if (it + 1 < T) load_group(it + 1);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    acc[0] = fmaf(-qv[u], ra[u].x, acc[0]); acc[1] = fmaf(-qv[u], ra[u].y, acc[1]);
-                    acc[2] = fmaf(-qv[u], ra[u].z, acc[2]); acc[3] = fmaf(-qv[u], ra[u].w, acc[3]);
-                    acc[4] = fmaf(-qv[u], rb[u].x, acc[4]); acc[5] = fmaf(-qv[u], rb[u].y, acc[5]);
-                    acc[6] = fmaf(-qv[u], rb[u].z, acc[6]); acc[7] = fmaf(-qv[u], rb[u].w, acc[7]);
+                for (int u = 0; u < 4; ++u) {
+                    const float qq[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
+                    const float rr[8] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w,
+                                         rb[u].x, rb[u].y, rb[u].z, rb[u].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) acc[i][q] = fmaf(-qq[i], rr[q], acc[i][q]);
                 }
             }
         }
-        // forward substitution against the diagonal block; column k = 4*kq + kp is owned by part kp.
-        // The rows of the diagonal block needed by 4 consecutive k are loaded ahead of the
-        // dependent multiply / shuffle / FMA chain.
+        // forward substitution against the diagonal block; column k = 4 kq + kp is owned by part kp
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq) {
             float4 da[4], db[4];
@@ -478,31 +457,33 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
             }
 #pragma unroll
             for (int kp = 0; kp < 4; ++kp) {
-                float qk = acc[kq] * rv[kp];
-                qk = __shfl_sync(0xffffffffu, qk, (lane & ~3) | kp);
-                if (p == kp) acc[kq] = qk;
                 const float rr[8] = {da[kp].x, da[kp].y, da[kp].z, da[kp].w,
                                      db[kp].x, db[kp].y, db[kp].z, db[kp].w};
 #pragma unroll
-                for (int q = kq; q < 8; ++q) {
-                    // column 4q + p is updated iff it lies to the right of column k = 4 kq + kp
-                    if (q > kq || p > kp) acc[q] = fmaf(-qk, rr[q], acc[q]);
+                for (int i = 0; i < 4; ++i) {
+                    float qk = acc[i][kq] * rv[kp];
+                    qk = __shfl_sync(0xffffffffu, qk, (lane & ~3) | kp);
+                    if (p == kp) acc[i][kq] = qk;
+#pragma unroll
+                    for (int q = kq; q < 8; ++q) {
+                        // column 4 q + p is updated iff it lies to the right of column 4 kq + kp
+                        if (q > kq || p > kp) acc[i][q] = fmaf(-qk, rr[q], acc[i][q]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) s.Q[jb * 32 + 4 * q + p][r] = acc[q];
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(&s.Q[jb * 32 + 4 * q + p][4 * rg]) =
+                make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
         __syncthreads();
-        // write block jb out (coalesced), fp32 in place and the fp16 shadow
-        {
-            const int sr = tid & (APPLY_ROWS - 1), sc0 = tid >> 6;
-            if (row0 + sr < m) {
-#pragma unroll
-                for (int c = sc0; c < 32; c += 4) {
-                    const float v = s.Q[jb * 32 + c][sr];
-                    A[row0 + sr + (long)(jb * 32 + c) * lda] = v;
-                    if (Qh) Qh[row0 + sr + (long)(jb * 32 + c) * ldqh] = __float2half_rn(v);
-                }
+        // write block jb out (coalesced: thread = row), fp32 in place and the fp16 shadow
+        if (row_ok) {
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) {
+                const float v = s.Q[jb * 32 + c][tid];
+                A[row0 + tid + (long)(jb * 32 + c) * lda] = v;
+                if (Qh) Qh[row0 + tid + (long)(jb * 32 + c) * ldqh] = __float2half_rn(v);
             }
         }
     }
@@ -529,16 +510,12 @@ ScratchLayout scratch_layout(int m, int num_sms) {
     return L;
 }
 
-constexpr int GRAM_SMEM = GRAM_ELEMS * (int)sizeof(double);   // combine buffer (> 16x160 staging tile)
 
 }  // namespace
 
 size_t panel_scratch_bytes(int m, int num_sms) { return scratch_layout(m, num_sms).total; }
 
 cudaError_t panel_init() {
-    cudaError_t e = cudaFuncSetAttribute(gram128_f64_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
-    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(apply128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(ApplySmem));
 }
@@ -554,7 +531,7 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
     const int ggrid = gram_grid(m, num_sms);
 
     cudaError_t le;
-    gram128_f64_kernel<<<ggrid, GRAM_THREADS, GRAM_SMEM, stream>>>(A, lda, m, part);
+    gram128_f64_kernel<<<ggrid, GRAM_THREADS, 0, stream>>>(A, lda, m, part);
     if ((le = cudaGetLastError()) != cudaSuccess) { fprintf(stderr, "later_b200: gram128 launch: %s\n", cudaGetErrorString(le)); return le; }
     gram128_reduce_kernel<<<(GRAM_ELEMS + 31) / 32, 1024, 0, stream>>>(part, ggrid, G, fac->flag);
     if ((le = cudaGetLastError()) != cudaSuccess) { fprintf(stderr, "later_b200: gram reduce launch: %s\n", cudaGetErrorString(le)); return le; }
