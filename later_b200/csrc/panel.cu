@@ -202,17 +202,23 @@ __device__ __forceinline__ double rsqrt_f64(double x) {
 
 // R = chol(G)^T in fp64, one CTA of 256 threads.  Thread (tx = column residue mod 16, ty = row
 // residue mod 16) keeps the elements (i, j) = (ty + 16 ia, tx + 16 jb), ia >= jb, of the trailing
-// lower triangle in registers (36 doubles).  Warp w holds tx in {w, w + 8} (one per half-warp), so
-// consecutive columns belong to different warps and a column's pivot is broadcast by shuffle.
-// Columns travel through a 4-slot shared-memory ring guarded by mbarriers: the owner of column c
-// derives it (pivot, reciprocal square root, scaling) as soon as column c-1 has been applied to ITS
-// entries; nobody waits at a block-wide barrier, the other warps' rank-1 updates run in the shadow
-// of the pivot chain.
+// lower triangle in registers (36 doubles).  Warp w holds tx in {2w, 2w + 1} (one per half-warp):
+// an even column c and its right neighbour c + 1 live in the same warp, which derives BOTH with
+// shuffles only (pivot, reciprocal square root, scaling; the update of column c+1 by column c never
+// leaves the warp).  Column pairs travel through a 4-slot shared-memory ring guarded by mbarriers,
+// every warp applies them as rank-2 updates; per-iteration costs (barrier wake-up, shared-memory
+// latency, output) are paid once per two columns and nobody waits at a block-wide barrier.
 struct CholShared {
-    double col[4][PW];
+    double col[4][2][PW];
     uint64_t full[4];
     uint64_t empty[4];
     float rinv[PW];
+#ifdef LB_CHOL_TRACE
+    long long t_pub[PW];
+    long long t_emit[PW];
+    long long t_wait[8][PW];
+    long long t_iter[8][PW];
+#endif
 };
 
 struct CholOut {
@@ -222,9 +228,7 @@ struct CholOut {
 };
 
 // Writes column k of L (= row k of R) to the caller's R and to the factor blocks.
-__device__ __forceinline__ void chol_output_column(int k, int q, const double* colk, const CholOut& o) {
-    if (q >= PW) return;
-    const int i = q;
+__device__ __forceinline__ void chol_output_column(int k, int i, const double* colk, const CholOut& o) {
     if (i < k) { o.R[k + (long)i * o.ldr] = 0.f; return; }        // strictly lower part of R
     const float l = (float)colk[i];
     o.R[k + (long)i * o.ldr] = l;                                  // R(k, i) = L(i, k)
@@ -233,64 +237,102 @@ __device__ __forceinline__ void chol_output_column(int k, int q, const double* c
     else o.fac->Roff[off_index(rb, ib)][rr][perm32(i & 31)] = l;
 }
 
+// Derives columns c (even) and c + 1 and publishes the pair.  This is the serial chain of the
+// factorisation; everything not needed by the other warps happens after the arrive.
 template <int CB>
-__device__ __forceinline__ void chol_emit_column(double (&a)[8][8], int c, int tx, int ty, int lane,
-                                                 CholShared& sh, const CholOut& o) {
-    // whole owner warp; the owner half-warp is the one with tx == c % 16
-    const int cr = c & 15;
-    double piv = a[CB][CB];
-    piv = __shfl_sync(0xffffffffu, piv, ((cr >> 3) << 4) | cr);   // lane with tx == cr, ty == cr
-    const int slot = c & 3;
-    if (c >= 4) mbar_wait(smem_u32(&sh.empty[slot]), ((c >> 2) & 1) ^ 1u);   // readers of c-4 done
-    if (tx == cr) {
-        if (!(piv > 0.0)) {                    // breakdown: numerically rank-deficient panel
-            if (ty == 0) atomicExch(o.info, c + 1);
-            piv = 1e-300;
-        }
-        const double rs = rsqrt_f64(piv);
+__device__ __forceinline__ void chol_emit_pair(double (&a)[8][8], int c, int ty, int lane,
+                                               CholShared& sh, const CholOut& o) {
+    const int cr = c & 15;                     // even; column c lives in half-warp 0, c+1 in half 1
+    const int half = lane >> 4;
+#ifdef LB_CHOL_TRACE
+    const long long te0 = clock64();
+#endif
+    const double piv0 = __shfl_sync(0xffffffffu, a[CB][CB], cr);            // half 0, ty == cr
+    const bool bad0 = !(piv0 > 0.0);
+    const double rs0 = rsqrt_f64(bad0 ? 1e-300 : piv0);
+    double l0[8];
 #pragma unroll
-        for (int ia = 0; ia < 8; ++ia) {
-            const int i = ty + 16 * ia;
-            double l = 0.0;
-            if (ia >= CB && i >= c) l = (i == c) ? piv * rs : a[ia][CB] * rs;
-            sh.col[slot][i] = l;
-        }
-        if (ty == cr) sh.rinv[c] = (float)rs;
+    for (int ia = CB; ia < 8; ++ia) l0[ia] = a[ia][CB] * rs0;               // meaningful in half 0
+    l0[CB] = (ty < cr) ? 0.0 : l0[CB];
+    // column c applied to column c + 1 inside the warp
+    const double lc1 = __shfl_sync(0xffffffffu, l0[CB], cr + 1);           // L(c+1, c)
+    double v[8];
+#pragma unroll
+    for (int ia = CB; ia < 8; ++ia) v[ia] = __shfl_sync(0xffffffffu, l0[ia], ty);   // same row, half 0
+    double a1[8];
+#pragma unroll
+    for (int ia = CB; ia < 8; ++ia) a1[ia] = fma(-v[ia], lc1, a[ia][CB]);   // meaningful in half 1
+    const double piv1 = __shfl_sync(0xffffffffu, a1[CB], 16 + cr + 1);     // half 1, ty == cr + 1
+    const bool bad1 = !(piv1 > 0.0);
+    const double rs1 = rsqrt_f64(bad1 ? 1e-300 : piv1);
+    const int slot = (c >> 1) & 3;
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia) {
+        double l = 0.0;
+        if (ia >= CB) l = half ? a1[ia] * rs1 : l0[ia];
+        if (ia == CB && half && ty < cr + 1) l = 0.0;
+        sh.col[slot][half][ty + 16 * ia] = l;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&sh.full[slot]));
+    // off the chain: bookkeeping
+    if (lane == cr) { sh.rinv[c] = (float)rs0; if (bad0) atomicExch(o.info, c + 1); }
+    if (lane == 16 + cr + 1) { sh.rinv[c + 1] = (float)rs1; if (bad1) atomicExch(o.info, c + 2); }
+#ifdef LB_CHOL_TRACE
+    if (lane == 0) { sh.t_pub[c] = clock64(); sh.t_emit[c] = clock64() - te0; }
+#endif
 }
 
 template <int CB>
 __device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, int tx, int ty,
                                                   int lane, CholShared& sh, const CholOut& o) {
 #pragma unroll 1
-    for (int cr = (CB == 0 ? 1 : 0); cr < 16; ++cr) {
-        const int c = CB * 16 + cr, k = c - 1;
-        const int slot = k & 3;
-        mbar_wait(smem_u32(&sh.full[slot]), (k >> 2) & 1u);       // column k has been published
-        double ci[8], cj[8];
+    for (int cr = (CB == 0 ? 2 : 0); cr < 16; cr += 2) {
+        const int c = CB * 16 + cr;            // pair (c, c+1) to derive; pair (c-2, c-1) to apply
+        const int ps = ((c >> 1) - 1) & 3;     // ring slot of the previous pair
+        const int owner = cr >> 1;
+#ifdef LB_CHOL_TRACE
+        const long long tw0 = clock64();
+#endif
+        // the owner makes sure its ring slot is free (readers of pair c/2 - 4 are done) while it
+        // would be waiting for the previous pair anyway
+        if (warp == owner && c >= 8) mbar_wait(smem_u32(&sh.empty[(c >> 1) & 3]), ((c >> 3) & 1) ^ 1u);
+        mbar_wait(smem_u32(&sh.full[ps]), (((c >> 1) - 1) >> 2) & 1u);     // previous pair published
+#ifdef LB_CHOL_TRACE
+        const long long tw1 = clock64();
+#endif
+        double ci0[8], ci1[8], cj0[8], cj1[8];
 #pragma unroll
         for (int q = CB; q < 8; ++q) {
-            ci[q] = sh.col[slot][ty + 16 * q];
-            cj[q] = sh.col[slot][tx + 16 * q];
+            ci0[q] = sh.col[ps][0][ty + 16 * q];
+            ci1[q] = sh.col[ps][1][ty + 16 * q];
+            cj0[q] = sh.col[ps][0][tx + 16 * q];
+            cj1[q] = sh.col[ps][1][tx + 16 * q];
         }
-        // block column CB first (it contains column c) so that its owner can derive column c
+        // block column CB first (it contains columns c, c+1) so that its owner can derive them
 #pragma unroll
-        for (int ia = CB; ia < 8; ++ia) a[ia][CB] = fma(-ci[ia], cj[CB], a[ia][CB]);
-        const int owner = cr & 7;
+        for (int ia = CB; ia < 8; ++ia)
+            a[ia][CB] = fma(-ci1[ia], cj1[CB], fma(-ci0[ia], cj0[CB], a[ia][CB]));
         if (warp == owner) {
-            chol_emit_column<CB>(a, c, tx, ty, lane, sh, o);
+            chol_emit_pair<CB>(a, c, ty, lane, sh, o);
         } else {
-            chol_output_column(k, (((warp - owner - 1) & 7) << 5) + lane, sh.col[slot], o);
+            const int rel = (warp - owner - 1) & 7;                 // 0..6 among the other warps
+            if (rel < 4) {
+                chol_output_column(c - 2, rel * 32 + lane, sh.col[ps][0], o);
+                chol_output_column(c - 1, rel * 32 + lane, sh.col[ps][1], o);
+            }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sh.empty[slot]));    // this warp is done reading column k
-        // rest of the rank-1 update
+        if (lane == 0) mbar_arrive(smem_u32(&sh.empty[ps]));        // done reading the previous pair
+        // rest of the rank-2 update
 #pragma unroll
         for (int jb = CB + 1; jb < 8; ++jb)
 #pragma unroll
-            for (int ia = jb; ia < 8; ++ia) a[ia][jb] = fma(-ci[ia], cj[jb], a[ia][jb]);
+            for (int ia = jb; ia < 8; ++ia)
+                a[ia][jb] = fma(-ci1[ia], cj1[jb], fma(-ci0[ia], cj0[jb], a[ia][jb]));
+#ifdef LB_CHOL_TRACE
+        if (lane == 0) { sh.t_wait[warp][c] = tw1 - tw0; sh.t_iter[warp][c] = clock64() - tw0; }
+#endif
         if ((c & 31) == 0) {
             // block-row (c/32 - 1) of R is complete once column c-1 has been written out
             __threadfence();
@@ -311,7 +353,7 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
                PanelFactors* __restrict__ fac, int* __restrict__ info) {
     __shared__ CholShared sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = warp + ((lane >> 4) << 3);   // column residue
+    const int tx = 2 * warp + (lane >> 4);      // column residue
     const int ty = lane & 15;                   // row residue
     const CholOut o{R, ldr, fac, info};
     // let the dependent apply kernel start right away: it synchronises on fac->flag[], not on
@@ -331,7 +373,7 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
             a[ia][jb] = (ia >= jb && i >= j) ? gram_elem(G, i, j) : 0.0;
         }
     __syncthreads();
-    if (warp == 0) chol_emit_column<0>(a, 0, tx, ty, lane, sh, o);   // column 0 needs no update
+    if (warp == 0) chol_emit_pair<0>(a, 0, ty, lane, sh, o);   // columns 0, 1 need no update
     chol_block_column<0>(a, warp, tx, ty, lane, sh, o);
     chol_block_column<1>(a, warp, tx, ty, lane, sh, o);
     chol_block_column<2>(a, warp, tx, ty, lane, sh, o);
@@ -340,9 +382,13 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
     chol_block_column<5>(a, warp, tx, ty, lane, sh, o);
     chol_block_column<6>(a, warp, tx, ty, lane, sh, o);
     chol_block_column<7>(a, warp, tx, ty, lane, sh, o);
-    // last column and last block-row
-    mbar_wait(smem_u32(&sh.full[(PW - 1) & 3]), ((PW - 1) >> 2) & 1u);
-    chol_output_column(PW - 1, threadIdx.x, sh.col[(PW - 1) & 3], o);
+    // last pair and last block-row
+    constexpr int LS = ((PW >> 1) - 1) & 3;
+    mbar_wait(smem_u32(&sh.full[LS]), (((PW >> 1) - 1) >> 2) & 1u);
+    if (threadIdx.x < PW) {
+        chol_output_column(PW - 2, threadIdx.x, sh.col[LS][0], o);
+        chol_output_column(PW - 1, threadIdx.x, sh.col[LS][1], o);
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -351,6 +397,22 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
         __syncwarp();
         if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&fac->flag[3]) = 1;
     }
+#ifdef LB_CHOL_TRACE
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int cb = 0; cb < 8; ++cb) {
+            long long dp = 0, em = 0, w[8] = {0}, it[8] = {0};
+            int n = 0;
+            for (int c = cb * 16 + (cb == 0 ? 4 : 0); c < cb * 16 + 16; c += 2) {
+                dp += sh.t_pub[c] - sh.t_pub[c - 2]; em += sh.t_emit[c]; ++n;
+                for (int q = 0; q < 8; ++q) { w[q] += sh.t_wait[q][c]; it[q] += sh.t_iter[q][c]; }
+            }
+            printf("CB %d: pair pub-to-pub %lld  emit %lld | wait/iter per warp:", cb, dp / n, em / n);
+            for (int q = 0; q < 8; ++q) printf(" %lld/%lld", w[q] / n, it[q] / n);
+            printf("\n");
+        }
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -364,7 +426,7 @@ constexpr int APPLY_ROWS = 128;
 constexpr int APPLY_THREADS = APPLY_ROWS;        // (APPLY_ROWS / 4) row groups x 4 column parts
 constexpr int APPLY_LDQ = APPLY_ROWS + 8;        // 136 floats: parts p = 0..3 land 8 banks apart
 struct ApplySmem {
-    float Q[PW][APPLY_LDQ];    // staged row block, column-major
+    float Q[96][APPLY_LDQ];    // finished blocks 0..2 of the row block (for the projections)
     float Rb[4][32][32];       // R(0..jb-1, jb) blocks of the current stage, [3] = diagonal block
     float rinv[32];
 };
@@ -375,23 +437,39 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(APPLY_THREADS)
+__global__ void __launch_bounds__(APPLY_THREADS, 3)
 apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __restrict__ fac,
                 __half* __restrict__ Qh, long ldqh) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     ApplySmem& s = *reinterpret_cast<ApplySmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * APPLY_ROWS;
     const int rg = tid >> 2, p = tid & 3;    // row group (rows 4 rg ..), column part
     const int lane = tid & 31;
-    const bool row_ok = row0 + tid < m;      // staging / write-out mapping: thread = row
-
-    // stage the row block (coalesced: a warp reads 32 consecutive rows of one column)
-#pragma unroll 16
-    for (int c = 0; c < PW; ++c) s.Q[c][tid] = row_ok ? A[row0 + tid + (long)c * lda] : 0.f;
+    const int grow = blockIdx.x * APPLY_ROWS + 4 * rg;   // first global row of this thread's tile
+    const int nvalid = min(4, max(0, m - grow));         // rows of this tile inside the matrix
+    const bool rows_ok = nvalid == 4;
+    const bool vec_a = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool vec_h = Qh && (ldqh % 4 == 0) && ((reinterpret_cast<uintptr_t>(Qh) & 7) == 0);
 
 #pragma unroll 1
     for (int jb = 0; jb < 4; ++jb) {
+        // this thread's 4 x 8 tile of block jb straight from global memory (a warp touches four
+        // columns x 128 contiguous bytes per request); issued before the wait so it overlaps it
+        float acc[4][8];                         // [row][q]: column 4 q + p of block jb
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float* src = A + grow + (long)(jb * 32 + 4 * q + p) * lda;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rows_ok && vec_a) {
+                v = *reinterpret_cast<const float4*>(src);
+            } else {
+                if (nvalid > 0) v.x = src[0];
+                if (nvalid > 1) v.y = src[1];
+                if (nvalid > 2) v.z = src[2];
+                if (nvalid > 3) v.w = src[3];
+            }
+            acc[0][q] = v.x; acc[1][q] = v.y; acc[2][q] = v.z; acc[3][q] = v.w;
+        }
         // wait until the Cholesky kernel has published block-row jb of R
         if (tid == 0) {
             while (ld_acquire(&fac->flag[jb]) == 0) { __nanosleep(64); }
@@ -406,12 +484,6 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
         if (tid < 32) s.rinv[tid] = __ldcg(&fac->rinv[jb * 32 + tid]);
         __syncthreads();
 
-        float acc[4][8];                         // [row][q]: column 4 q + p of block jb
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(&s.Q[jb * 32 + 4 * q + p][4 * rg]);
-            acc[0][q] = v.x; acc[1][q] = v.y; acc[2][q] = v.z; acc[3][q] = v.w;
-        }
         // project out the finished blocks, software-pipelined over groups of 4 k-steps
         {
             const int T = jb * 8;                // groups of 4 consecutive k over all ib < jb
@@ -472,18 +544,32 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
                 }
             }
         }
+        // finished block: to global (fp32 in place + fp16 shadow) and, for the later projections,
+        // to shared memory
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(&s.Q[jb * 32 + 4 * q + p][4 * rg]) =
-                make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
-        __syncthreads();
-        // write block jb out (coalesced: thread = row), fp32 in place and the fp16 shadow
-        if (row_ok) {
-#pragma unroll 8
-            for (int c = 0; c < 32; ++c) {
-                const float v = s.Q[jb * 32 + c][tid];
-                A[row0 + tid + (long)(jb * 32 + c) * lda] = v;
-                if (Qh) Qh[row0 + tid + (long)(jb * 32 + c) * ldqh] = __float2half_rn(v);
+        for (int q = 0; q < 8; ++q) {
+            const int c = jb * 32 + 4 * q + p;
+            const float4 v = make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
+            if (jb < 3) *reinterpret_cast<float4*>(&s.Q[c][4 * rg]) = v;
+            if (nvalid > 0) {
+                float* dst = A + grow + (long)c * lda;
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+                if (rows_ok && vec_a) *reinterpret_cast<float4*>(dst) = v;
+                else for (int i = 0; i < nvalid; ++i) dst[i] = vv[i];
+                if (Qh) {
+                    __half* hd = Qh + grow + (long)c * ldqh;
+                    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+                    if (rows_ok && vec_h) {
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                        pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        *reinterpret_cast<uint2*>(hd) = pk;
+                    } else {
+                        const __half hh[4] = {__low2half(h01), __high2half(h01), __low2half(h23),
+                                              __high2half(h23)};
+                        for (int i = 0; i < nvalid; ++i) hd[i] = hh[i];
+                    }
+                }
             }
         }
     }
