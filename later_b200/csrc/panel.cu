@@ -11,6 +11,7 @@
 //                         Cholesky kernel and consumes each 32-row block of R as soon as its flag is
 //                         raised; writes Q (fp32, in place) and its fp16 shadow
 #include "panel.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -116,6 +117,8 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
         }
     };
 
+    pdl_trigger();
+    pdl_wait();      // the panel is written by the preceding update kernel
     int chunk = blockIdx.x;
     if (chunk < nchunks) prefetch(chunk);
     for (; chunk < nchunks; chunk += gridDim.x) {
@@ -171,6 +174,8 @@ gram128_reduce_kernel(const double* __restrict__ part, int nparts, double* __res
     __shared__ double sh[32][33];
     const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int idx = blockIdx.x * 32 + e;
+    pdl_trigger();
+    pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x < 4) flags[threadIdx.x] = 0;
     double s = 0.0;
     if (idx < GRAM_ELEMS)
@@ -356,14 +361,15 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
     const int tx = 2 * warp + (lane >> 4);      // column residue
     const int ty = lane & 15;                   // row residue
     const CholOut o{R, ldr, fac, info};
-    // let the dependent apply kernel start right away: it synchronises on fac->flag[], not on
-    // the completion of this grid
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&sh.full[s]), 1); mbar_init(smem_u32(&sh.empty[s]), 8); }
         fence_barrier_init();
     }
+    pdl_wait();      // G and the cleared flags come from the reduce kernel
+    // Only now may the dependent apply grid start: it synchronises on fac->flag[] (not on the
+    // completion of this grid), so the flags must already have been cleared by the reduce kernel.
+    pdl_trigger();
     double a[8][8];
 #pragma unroll
     for (int ia = 0; ia < 8; ++ia)
@@ -450,6 +456,7 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
     const bool rows_ok = nvalid == 4;
     const bool vec_a = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const bool vec_h = Qh && (ldqh % 4 == 0) && ((reinterpret_cast<uintptr_t>(Qh) & 7) == 0);
+    pdl_trigger();   // (no pdl_wait: this grid synchronises with the Cholesky grid through flags)
 
 #pragma unroll 1
     for (int jb = 0; jb < 4; ++jb) {
@@ -617,12 +624,12 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
     const int ggrid = gram_grid(m, num_sms);
 
     cudaError_t le;
-    gram128_f64_kernel<<<ggrid, GRAM_THREADS, 0, stream>>>(A, lda, m, part);
-    if ((le = cudaGetLastError()) != cudaSuccess) { fprintf(stderr, "later_b200: gram128 launch: %s\n", cudaGetErrorString(le)); return le; }
-    gram128_reduce_kernel<<<(GRAM_ELEMS + 31) / 32, 1024, 0, stream>>>(part, ggrid, G, fac->flag);
-    if ((le = cudaGetLastError()) != cudaSuccess) { fprintf(stderr, "later_b200: gram reduce launch: %s\n", cudaGetErrorString(le)); return le; }
-    chol128_kernel<<<1, 256, 0, stream>>>(G, R, ldr, fac, info);
-    if ((le = cudaGetLastError()) != cudaSuccess) { fprintf(stderr, "later_b200: chol128 launch: %s\n", cudaGetErrorString(le)); return le; }
+    if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream,
+                         (const float*)A, lda, m, part)) != cudaSuccess) return le;
+    if ((le = launch_pdl(gram128_reduce_kernel, dim3((GRAM_ELEMS + 31) / 32), dim3(1024), 0, stream,
+                         (const double*)part, ggrid, G, fac->flag)) != cudaSuccess) return le;
+    if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(256), 0, stream, (const double*)G, R, ldr, fac,
+                         info)) != cudaSuccess) return le;
     // programmatic dependent launch: the apply grid may start while the Cholesky grid is running
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((m + APPLY_ROWS - 1) / APPLY_ROWS);

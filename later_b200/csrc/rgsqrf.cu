@@ -20,6 +20,7 @@
 #include <new>
 
 #include "context.h"
+#include "launch.cuh"
 #include "panel.cuh"
 #include "tc_gemm.cuh"
 
@@ -45,6 +46,8 @@ inline long round_up(long x, long a) { return (x + a - 1) / a * a; }
 __global__ void cast_shadow_kernel(const float* __restrict__ A, long lda, int m, int c0, int n,
                                    __half* __restrict__ Qh, long ldh, int vec_ok) {
     const int col = c0 + blockIdx.y;
+    pdl_trigger();
+    pdl_wait();
     if (col >= n) return;
     const float* src = A + (long)col * lda;
     __half* dst = Qh + (long)col * ldh;
@@ -66,6 +69,16 @@ __global__ void cast_shadow_kernel(const float* __restrict__ A, long lda, int m,
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
             dst[i] = __float2half_rn(src[i]);
     }
+}
+
+// Strictly lower triangle of R := 0 (the algorithm never produces it; the reference leaves it
+// untouched and relies on a fresh cudaMalloc, test/test_qr.cu:49-50).
+__global__ void zero_lower_kernel(float* __restrict__ R, long ldr, int n) {
+    pdl_trigger();
+    pdl_wait();
+    const int j = blockIdx.y;
+    for (int i = j + 1 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        R[i + (long)j * ldr] = 0.f;
 }
 
 struct Workspace {
@@ -121,10 +134,6 @@ struct Recursion {
         if (err != cudaSuccess) return;
         const int bn = gram_bn(h);
         float* R12 = p->R + c0 + (long)(c0 + h) * p->ldr;
-        // R21 block is never produced by the algorithm: make it an explicit zero (the reference
-        // leaves it untouched and relies on a fresh cudaMalloc, test/test_qr.cu:49-50).
-        check(cudaMemset2DAsync(p->R + (c0 + h) + (long)c0 * p->ldr, (size_t)p->ldr * sizeof(float),
-                                0, (size_t)h * sizeof(float), h, st));
         // R12 = Q1^T A2 (fp32 into R, fp16 copy for the update)
         const int splits = choose_gram_splits(ctx->num_sms, h, h, bn, p->m);
         check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, c0 + h, h,
@@ -199,9 +208,14 @@ int enqueue_factorisation(later_b200_ctx* ctx, long* launches) {
     if (p.n > NMIN) {
         const int vec_ok = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
         dim3 grid((unsigned)std::min<long>((p.m / 8 + 255) / 256, 64), (unsigned)(p.n - NMIN));
-        cast_shadow_kernel<<<grid, 256, 0, ctx->stream>>>(p.A, p.lda, p.m, NMIN, p.n, p.Qh, p.ldh,
-                                                          vec_ok);
-        rec.launches += 1;
+        if ((e = launch_pdl(cast_shadow_kernel, grid, dim3(256), 0, ctx->stream, (const float*)p.A,
+                            (long)p.lda, p.m, NMIN, p.n, p.Qh, p.ldh, vec_ok)) != cudaSuccess)
+            return cuda_fail(ctx, e, "cast launch");
+        dim3 zgrid((unsigned)std::min(8, (p.n + 255) / 256), (unsigned)p.n);
+        if ((e = launch_pdl(zero_lower_kernel, zgrid, dim3(256), 0, ctx->stream, p.R, (long)p.ldr,
+                            p.n)) != cudaSuccess)
+            return cuda_fail(ctx, e, "zero launch");
+        rec.launches += 2;
     }
     rec.qr(0, p.n);
     if (rec.err != cudaSuccess) return cuda_fail(ctx, rec.err, "rgsqrf enqueue");

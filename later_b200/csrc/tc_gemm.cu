@@ -12,6 +12,7 @@
 // The accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
 #include "tc_gemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -98,6 +99,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_trigger();   // the next kernel may start its prologue
+    pdl_wait();      // operands are written by the predecessors
 
     const int tiles = p.tiles_m * p.tiles_n;
     const int items = tiles * p.splits;
@@ -248,6 +251,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
                                      float* __restrict__ C, long ldc, __half* __restrict__ Ch,
                                      long ldch) {
     const long total = (long)M * N;
+    pdl_trigger();
+    pdl_wait();
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
          idx += (long)gridDim.x * blockDim.x) {
         float s = 0.f;
@@ -290,8 +295,9 @@ cudaError_t launch(cudaStream_t stream, int num_sms, const CUtensorMap& mapA,
                    const CUtensorMap& mapB, const TcGemmParams& p) {
     const int items = p.tiles_m * p.tiles_n * p.splits;
     const int grid = std::max(1, std::min(items, num_sms));
-    tc_gemm_kernel<BN, A_MN, EPI><<<grid, kThreads, Cfg<BN>::SMEM_BYTES, stream>>>(mapA, mapB, p);
-    return cudaGetLastError();
+    cudaError_t e = launch_pdl(tc_gemm_kernel<BN, A_MN, EPI>, dim3(grid), dim3(kThreads),
+                               (size_t)Cfg<BN>::SMEM_BYTES, stream, mapA, mapB, p);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace
@@ -442,8 +448,9 @@ cudaError_t splitk_reduce(cudaStream_t stream, const float* part, int splits, in
     const long total = (long)M * N;
     const int threads = 256;
     const int blocks = (int)std::min<long>((total + threads - 1) / threads, 148L * 8);
-    splitk_reduce_kernel<<<blocks, threads, 0, stream>>>(part, splits, M, N, C, ldc, Ch, ldch);
-    return cudaGetLastError();
+    cudaError_t e = launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(threads), 0, stream, part, splits,
+                               M, N, C, ldc, Ch, ldch);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace lb

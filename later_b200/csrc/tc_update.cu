@@ -11,6 +11,7 @@
 //               fp16 shadow next to it, fence.proxy.async, then one thread issues the two TMA stores
 //               (fp32 C and fp16 shadow) and recycles the slot once the stores have read it.
 #include "tc_gemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -115,6 +116,8 @@ tc_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int tiles = p.tiles_m * p.tiles_n;
+    pdl_trigger();   // the next kernel may start its prologue
+    pdl_wait();      // operands and C are written by the predecessors
 
     if (warp == 0) {
         // ------------------------------------------------------------------ A/B producer
@@ -299,9 +302,9 @@ cudaError_t launch_u(cudaStream_t stream, int num_sms, const CUtensorMap& a, con
                      const CUtensorMap& c, const CUtensorMap& h, const UpdParams& p) {
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = std::max(1, std::min(tiles, num_sms));
-    tc_update_kernel<BN, CCH, CSLOTS, SUB, SHADOW>
-        <<<grid, kThreads, UCfg<BN, CCH, CSLOTS>::SMEM_BYTES, stream>>>(a, b, c, h, p);
-    return cudaGetLastError();
+    cudaError_t e = launch_pdl(tc_update_kernel<BN, CCH, CSLOTS, SUB, SHADOW>, dim3(grid), dim3(kThreads),
+                               (size_t)UCfg<BN, CCH, CSLOTS>::SMEM_BYTES, stream, a, b, c, h, p);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <int BN, int CCH, int CSLOTS, bool SUB, bool SHADOW>
