@@ -32,10 +32,17 @@ struct later_b200_ctx {
         bool valid = false;
     } plan;
 
-    // One cached executable graph (the shapes and pointers of the last factorisation).
-    cudaGraphExec_t graph_exec = nullptr;
-    Plan graph_plan;
-    long graph_launches = 0;
+    // Cached executable graphs: [0] whole factorisation, [1] left recursion, [2] the rest
+    // (the two halves are used by the pipelined host entry point).
+    struct GraphSlot {
+        cudaGraphExec_t exec = nullptr;
+        Plan plan;
+        long launches = 0;
+    } graphs[3];
+
+    // pipelined host path: copy streams and events
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // device staging buffers for the *_host entry point
     float* dA = nullptr; size_t dA_bytes = 0;

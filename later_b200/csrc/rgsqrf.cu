@@ -129,9 +129,15 @@ struct Recursion {
             launches += 4;
             return;
         }
-        const int h = w / 2;
-        qr(c0, h);
+        qr(c0, w / 2);
+        node_tail(c0, w);
+    }
+
+    // Everything of node (c0, w) after its left recursion: R12 = Q1^T A2, A2 -= Q1 R12, right half.
+    void node_tail(int c0, int w) {
         if (err != cudaSuccess) return;
+        cudaStream_t st = ctx->stream;
+        const int h = w / 2;
         const int bn = gram_bn(h);
         float* R12 = p->R + c0 + (long)(c0 + h) * p->ldr;
         // R12 = Q1^T A2 (fp32 into R, fp16 copy for the update)
@@ -194,7 +200,12 @@ int prepare_plan(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R,
 }
 
 // Enqueues the whole factorisation on ctx->stream (directly, or into an ongoing capture).
-int enqueue_factorisation(later_b200_ctx* ctx, long* launches) {
+// Stages of one factorisation.  ALL is the whole thing; LEFT + REST are the same launches split at
+// the top node (left recursion | top-level gram + update + right recursion) so that the host entry
+// point can overlap them with the PCIe transfers of the other half.
+enum Stage : int { STAGE_ALL = 0, STAGE_LEFT = 1, STAGE_REST = 2 };
+
+int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
     auto& p = ctx->plan;
     Recursion rec{};
     rec.ctx = ctx;
@@ -205,19 +216,27 @@ int enqueue_factorisation(later_b200_ctx* ctx, long* launches) {
         (e = make_tensor_map_f16(&rec.q256, qm, 64, 256)) != cudaSuccess ||
         (e = make_tensor_map_f16(&rec.q64, qm, 64, 64)) != cudaSuccess)
         return cuda_fail(ctx, e, "tensor map encode");
-    if (p.n > NMIN) {
+    // fp16 shadow of the not-yet-factored input columns this stage will read as A2 operands
+    const int cast_lo = stage == STAGE_REST ? p.n / 2 : NMIN;
+    const int cast_hi = stage == STAGE_LEFT ? p.n / 2 : p.n;
+    if (cast_hi > cast_lo) {
         const int vec_ok = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-        dim3 grid((unsigned)std::min<long>((p.m / 8 + 255) / 256, 64), (unsigned)(p.n - NMIN));
+        dim3 grid((unsigned)std::min<long>((p.m / 8 + 255) / 256, 64), (unsigned)(cast_hi - cast_lo));
         if ((e = launch_pdl(cast_shadow_kernel, grid, dim3(256), 0, ctx->stream, (const float*)p.A,
-                            (long)p.lda, p.m, NMIN, p.n, p.Qh, p.ldh, vec_ok)) != cudaSuccess)
+                            (long)p.lda, p.m, cast_lo, cast_hi, p.Qh, p.ldh, vec_ok)) != cudaSuccess)
             return cuda_fail(ctx, e, "cast launch");
+        rec.launches += 1;
+    }
+    if (stage != STAGE_REST && p.n > NMIN) {
         dim3 zgrid((unsigned)std::min(8, (p.n + 255) / 256), (unsigned)p.n);
         if ((e = launch_pdl(zero_lower_kernel, zgrid, dim3(256), 0, ctx->stream, p.R, (long)p.ldr,
                             p.n)) != cudaSuccess)
             return cuda_fail(ctx, e, "zero launch");
-        rec.launches += 2;
+        rec.launches += 1;
     }
-    rec.qr(0, p.n);
+    if (stage == STAGE_ALL) rec.qr(0, p.n);
+    else if (stage == STAGE_LEFT) rec.qr(0, p.n / 2);
+    else rec.node_tail(0, p.n);
     if (rec.err != cudaSuccess) return cuda_fail(ctx, rec.err, "rgsqrf enqueue");
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "rgsqrf launch");
@@ -230,26 +249,26 @@ bool same_plan(const later_b200_ctx::Plan& a, const later_b200_ctx::Plan& b) {
            a.R == b.R && a.ldr == b.ldr && a.Qh == b.Qh && a.arena_gen == b.arena_gen;
 }
 
-int rgsqrf_device(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
-    int rc = validate(ctx, m, n, A, lda, R, ldr);
-    if (rc) return rc;
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
-    rc = prepare_plan(ctx, m, n, A, lda, R, ldr);
-    if (rc) return rc;
-
+// Runs one stage on ctx->stream: replays the cached graph of that stage when shapes and pointers
+// match, otherwise captures and instantiates it (or launches directly with graphs disabled).
+int run_stage(later_b200_ctx* ctx, int stage) {
+    cudaError_t e;
     if (!ctx->use_graph) {
-        return enqueue_factorisation(ctx, &ctx->launches);
+        long l = 0;
+        int rc = enqueue_stage(ctx, stage, &l);
+        ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + l;
+        return rc;
     }
-    if (ctx->graph_exec && same_plan(ctx->graph_plan, ctx->plan)) {
-        e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
+    auto& slot = ctx->graphs[stage];
+    if (slot.exec && same_plan(slot.plan, ctx->plan)) {
+        e = cudaGraphLaunch(slot.exec, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
-        ctx->launches = ctx->graph_launches;
+        ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + slot.launches;
         return 0;
     }
-    if (ctx->graph_exec) {
-        cudaGraphExecDestroy(ctx->graph_exec);
-        ctx->graph_exec = nullptr;
+    if (slot.exec) {
+        cudaGraphExecDestroy(slot.exec);
+        slot.exec = nullptr;
     }
     // Capture on a private stream so the legacy default stream can be the context's stream.
     cudaStream_t cap = nullptr;
@@ -259,23 +278,41 @@ int rgsqrf_device(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R
     ctx->stream = cap;
     long launches = 0;
     e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) { ctx->stream = user; cudaStreamDestroy(cap); return cuda_fail(ctx, e, "begin capture"); }
-    rc = enqueue_factorisation(ctx, &launches);
+    if (e != cudaSuccess) {
+        ctx->stream = user;
+        cudaStreamDestroy(cap);
+        return cuda_fail(ctx, e, "begin capture");
+    }
+    int rc = enqueue_stage(ctx, stage, &launches);
     cudaGraph_t graph = nullptr;
     e = cudaStreamEndCapture(cap, &graph);
     ctx->stream = user;
     cudaStreamDestroy(cap);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "end capture");
-    e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+    e = cudaGraphInstantiate(&slot.exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { ctx->graph_exec = nullptr; return cuda_fail(ctx, e, "graph instantiate"); }
-    ctx->graph_plan = ctx->plan;
-    ctx->graph_launches = launches;
-    ctx->launches = launches;
-    e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
+    if (e != cudaSuccess) { slot.exec = nullptr; return cuda_fail(ctx, e, "graph instantiate"); }
+    slot.plan = ctx->plan;
+    slot.launches = launches;
+    ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + launches;
+    e = cudaGraphLaunch(slot.exec, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
     return 0;
+}
+
+int rgsqrf_prepare(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
+    int rc = validate(ctx, m, n, A, lda, R, ldr);
+    if (rc) return rc;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    return prepare_plan(ctx, m, n, A, lda, R, ldr);
+}
+
+int rgsqrf_device(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
+    int rc = rgsqrf_prepare(ctx, m, n, A, lda, R, ldr);
+    if (rc) return rc;
+    return run_stage(ctx, STAGE_ALL);
 }
 
 __global__ void cast_matrix_kernel(const float* __restrict__ S, long lds, int rows, int cols,
@@ -335,7 +372,12 @@ int later_b200_destroy(later_b200_ctx* ctx) {
     if (!ctx) return LATER_B200_EINVAL;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    for (auto& g : ctx->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->dA) cudaFree(ctx->dA);
     if (ctx->dR) cudaFree(ctx->dR);
     ctx->arena.release();
@@ -384,18 +426,72 @@ int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda
         if ((e = cudaMalloc(&ctx->dR, r_bytes)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc R");
         ctx->dR_bytes = r_bytes;
     }
-    e = cudaMemcpy2DAsync(ctx->dA, (size_t)m * sizeof(float), hA, (size_t)lda * sizeof(float),
-                          (size_t)m * sizeof(float), n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "H2D A");
-    rc = rgsqrf_device(ctx, m, n, ctx->dA, m, ctx->dR, n);
-    if (rc) return rc;
-    e = cudaMemcpy2DAsync(hA, (size_t)lda * sizeof(float), ctx->dA, (size_t)m * sizeof(float),
-                          (size_t)m * sizeof(float), n, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpy2DAsync(hR, (size_t)ldr * sizeof(float), ctx->dR, (size_t)n * sizeof(float),
-                              (size_t)n * sizeof(float), n, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "D2H Q/R");
+    if (!ctx->s_in) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(ctx, e, "copy streams");
+        for (auto& ev : ctx->ev)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess)
+                return cuda_fail(ctx, e, "events");
+    }
+    float* dA = ctx->dA;
+    float* dR = ctx->dR;
+    const size_t colA = (size_t)m * sizeof(float), colR = (size_t)n * sizeof(float);
+    auto h2d = [&](int c0, int nc) {
+        return cudaMemcpy2DAsync(dA + (size_t)c0 * m, colA, hA + (size_t)c0 * lda,
+                                 (size_t)lda * sizeof(float), colA, nc, cudaMemcpyHostToDevice, ctx->s_in);
+    };
+    auto d2h_q = [&](int c0, int nc) {
+        return cudaMemcpy2DAsync(hA + (size_t)c0 * lda, (size_t)lda * sizeof(float), dA + (size_t)c0 * m,
+                                 colA, colA, nc, cudaMemcpyDeviceToHost, ctx->s_out);
+    };
+    auto d2h_r = [&](int r0, int nr, int c0, int nc) {
+        return cudaMemcpy2DAsync(hR + r0 + (size_t)c0 * ldr, (size_t)ldr * sizeof(float),
+                                 dR + r0 + (size_t)c0 * n, colR, (size_t)nr * sizeof(float), nc,
+                                 cudaMemcpyDeviceToHost, ctx->s_out);
+    };
+    // order the copies after whatever the caller already enqueued on the context's stream
+    if ((e = cudaEventRecord(ctx->ev[4], ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamWaitEvent(ctx->s_in, ctx->ev[4], 0)) != cudaSuccess ||
+        (e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[4], 0)) != cudaSuccess)
+        return cuda_fail(ctx, e, "stream ordering");
+    if ((rc = rgsqrf_prepare(ctx, m, n, dA, m, dR, n)) != 0) return rc;
+
+    if (n < 2 * NMIN) {
+        // single panel: nothing to overlap
+        if ((e = h2d(0, n)) != cudaSuccess || (e = cudaEventRecord(ctx->ev[0], ctx->s_in)) != cudaSuccess ||
+            (e = cudaStreamWaitEvent(ctx->stream, ctx->ev[0], 0)) != cudaSuccess)
+            return cuda_fail(ctx, e, "H2D A");
+        if ((rc = run_stage(ctx, STAGE_ALL)) != 0) return rc;
+        if ((e = cudaEventRecord(ctx->ev[2], ctx->stream)) != cudaSuccess ||
+            (e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[2], 0)) != cudaSuccess ||
+            (e = d2h_q(0, n)) != cudaSuccess || (e = d2h_r(0, n, 0, n)) != cudaSuccess)
+            return cuda_fail(ctx, e, "D2H Q/R");
+    } else {
+        // Pipelined: the left half of A is factored while the right half is still crossing PCIe;
+        // the left half of Q and R11 go back while the right half is being factored.
+        const int h = n / 2;
+        if ((e = h2d(0, h)) != cudaSuccess || (e = cudaEventRecord(ctx->ev[0], ctx->s_in)) != cudaSuccess ||
+            (e = h2d(h, n - h)) != cudaSuccess || (e = cudaEventRecord(ctx->ev[1], ctx->s_in)) != cudaSuccess)
+            return cuda_fail(ctx, e, "H2D A");
+        if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev[0], 0)) != cudaSuccess)
+            return cuda_fail(ctx, e, "wait H2D left");
+        if ((rc = run_stage(ctx, STAGE_LEFT)) != 0) return rc;
+        if ((e = cudaEventRecord(ctx->ev[2], ctx->stream)) != cudaSuccess ||
+            (e = cudaStreamWaitEvent(ctx->stream, ctx->ev[1], 0)) != cudaSuccess)
+            return cuda_fail(ctx, e, "wait H2D right");
+        if ((rc = run_stage(ctx, STAGE_REST)) != 0) return rc;
+        if ((e = cudaEventRecord(ctx->ev[3], ctx->stream)) != cudaSuccess)
+            return cuda_fail(ctx, e, "record");
+        if ((e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[2], 0)) != cudaSuccess ||
+            (e = d2h_q(0, h)) != cudaSuccess || (e = d2h_r(0, h, 0, h)) != cudaSuccess ||
+            (e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[3], 0)) != cudaSuccess ||
+            (e = d2h_q(h, n - h)) != cudaSuccess || (e = d2h_r(0, n, h, n - h)) != cudaSuccess ||
+            (e = d2h_r(h, n - h, 0, h)) != cudaSuccess)
+            return cuda_fail(ctx, e, "D2H Q/R");
+    }
+    if ((e = cudaStreamSynchronize(ctx->s_out)) != cudaSuccess) return cuda_fail(ctx, e, "D2H sync");
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return cuda_fail(ctx, e, "sync");
     return 0;
 }
 
