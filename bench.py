@@ -157,6 +157,8 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     distributed = world > 1 and args.impl == "b200"
     if distributed:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     if N == 1:

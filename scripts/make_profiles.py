@@ -46,7 +46,7 @@ for rep in sorted((ROOT / "gpurun_out").glob("*.ncu-rep")):
         traffic["tc_gemm_gram_top_tensor_pipe_pct"] = rows[0]["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]
 if traffic:
     (OUT / "traffic.json").write_text(json.dumps(traffic, indent=1))
-for name in ("launches_16k", "launches_1m", "launches_128k"):
+for name in ("launches_16k", "launches_1m", "launches_256k"):
     src = ROOT / "gpurun_out" / f"{name}.csv"
     if src.exists():
         agg = subprocess.run([sys.executable, str(ROOT / "scripts" / "agg_launches.py"), str(src), "2"], capture_output=True, text=True).stdout
