@@ -3,9 +3,10 @@
 //                         fp32 x fp32 products accumulated in fp64 on the fp64 tensor path
 //                         (mma.sync.m8n8k4.f64), per-CTA partial Gram blocks
 //   gram128_reduce_kernel fixed-order sum of the per-CTA partials (deterministic)
-//   chol128_kernel        R = chol(G) in fp64 on one CTA: trailing matrix in registers, columns
-//                         broadcast through an mbarrier-guarded shared-memory ring (no block-wide
-//                         barrier on the critical path); publishes R block-row by block-row
+//   chol128_kernel        R = chol(G) in fp64 on one CTA: trailing matrix in registers, two columns
+//                         per step derived inside one warp, column pairs broadcast through an
+//                         mbarrier-guarded shared-memory ring, a dedicated output warp publishes R
+//                         block-row by block-row
 //   apply128_kernel       Q = A R^-1 by forward substitution, four threads per matrix row; launched
 //                         with programmatic dependent launch so that it runs CONCURRENTLY with the
 //                         Cholesky kernel and consumes each 32-row block of R as soon as its flag is
@@ -148,10 +149,18 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
 #pragma unroll
                 for (int t = 0; t < 4; ++t) b[t] = As[ks * 4 + fr][bj * GW + t * 8 + fc];
             }
+            if (bi == bj) {
+                // diagonal block: only its upper tiles are ever read (G is symmetric)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_884(acc[i][j], a[i], b[j]);
+                    for (int j = i; j < 4; ++j) dmma_884(acc[i][j], a[i], b[j]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma_884(acc[i][j], a[i], b[j]);
+            }
         }
         __syncthreads();
     }
@@ -205,25 +214,20 @@ __device__ __forceinline__ double rsqrt_f64(double x) {
     return fma(0.5 * y, e, y);                 // one Newton step: ~2^-45 relative
 }
 
-// R = chol(G)^T in fp64, one CTA of 256 threads.  Thread (tx = column residue mod 16, ty = row
-// residue mod 16) keeps the elements (i, j) = (ty + 16 ia, tx + 16 jb), ia >= jb, of the trailing
-// lower triangle in registers (36 doubles).  Warp w holds tx in {2w, 2w + 1} (one per half-warp):
-// an even column c and its right neighbour c + 1 live in the same warp, which derives BOTH with
-// shuffles only (pivot, reciprocal square root, scaling; the update of column c+1 by column c never
-// leaves the warp).  Column pairs travel through a 4-slot shared-memory ring guarded by mbarriers,
-// every warp applies them as rank-2 updates; per-iteration costs (barrier wake-up, shared-memory
-// latency, output) are paid once per two columns and nobody waits at a block-wide barrier.
+// R = chol(G)^T in fp64, one CTA: 8 compute warps + 1 output warp.
+// Compute thread (tx = column residue mod 16, ty = row residue mod 16) keeps the elements
+// (i, j) = (ty + 16 ia, tx + 16 jb), ia >= jb, of the trailing lower triangle in registers (36
+// doubles).  Warp w holds tx in {2w, 2w + 1} (one per half-warp): an even column c and its right
+// neighbour c + 1 live in the same warp, which derives BOTH with shuffles only.  Column pairs travel
+// through a 4-slot shared-memory ring guarded by mbarriers and are applied by every compute warp as
+// rank-2 updates; the ninth warp does nothing but write finished columns (rows of R, the 32x32
+// factor blocks, 1/diag, the block-row flags) to global memory, so no compute warp ever leaves the
+// register/shared-memory domain and nobody waits at a block-wide barrier.
 struct CholShared {
     double col[4][2][PW];
+    double rs[PW];              // 1 / L(c, c), written by the owner before it publishes column c
     uint64_t full[4];
     uint64_t empty[4];
-    float rinv[PW];
-#ifdef LB_CHOL_TRACE
-    long long t_pub[PW];
-    long long t_emit[PW];
-    long long t_wait[8][PW];
-    long long t_iter[8][PW];
-#endif
 };
 
 struct CholOut {
@@ -232,60 +236,43 @@ struct CholOut {
     int* info;
 };
 
-// Writes column k of L (= row k of R) to the caller's R and to the factor blocks.
-__device__ __forceinline__ void chol_output_column(int k, int i, const double* colk, const CholOut& o) {
-    if (i < k) { o.R[k + (long)i * o.ldr] = 0.f; return; }        // strictly lower part of R
-    const float l = (float)colk[i];
-    o.R[k + (long)i * o.ldr] = l;                                  // R(k, i) = L(i, k)
-    const int rb = k >> 5, rr = k & 31, ib = i >> 5;
-    if (ib == rb) o.fac->Rdiag[rb][rr][perm32(i & 31)] = l;
-    else o.fac->Roff[off_index(rb, ib)][rr][perm32(i & 31)] = l;
-}
+constexpr int CHOL_THREADS = 9 * 32;
 
 // Derives columns c (even) and c + 1 and publishes the pair.  This is the serial chain of the
-// factorisation; everything not needed by the other warps happens after the arrive.
+// factorisation, so the two reciprocal square roots are made independent of each other:
+//   piv1 = a11 - a10^2 / piv0 = d / piv0,  d = a11 piv0 - a10^2
+//   => rsqrt(piv1) = rsqrt(d) * sqrt(piv0), and rsqrt(d), rsqrt(piv0) start together.
 template <int CB>
 __device__ __forceinline__ void chol_emit_pair(double (&a)[8][8], int c, int ty, int lane,
                                                CholShared& sh, const CholOut& o) {
     const int cr = c & 15;                     // even; column c lives in half-warp 0, c+1 in half 1
     const int half = lane >> 4;
-#ifdef LB_CHOL_TRACE
-    const long long te0 = clock64();
-#endif
-    const double piv0 = __shfl_sync(0xffffffffu, a[CB][CB], cr);            // half 0, ty == cr
+    const double piv0 = __shfl_sync(0xffffffffu, a[CB][CB], cr);            // (c, c)
+    const double a10 = __shfl_sync(0xffffffffu, a[CB][CB], cr + 1);         // (c+1, c)
+    const double a11 = __shfl_sync(0xffffffffu, a[CB][CB], 16 + cr + 1);    // (c+1, c+1)
+    double u[8];                               // unscaled column c, same row, for half-warp 1
+#pragma unroll
+    for (int ia = CB; ia < 8; ++ia) u[ia] = __shfl_sync(0xffffffffu, a[ia][CB], ty);
+    const double d = fma(a11, piv0, -a10 * a10);
     const bool bad0 = !(piv0 > 0.0);
-    const double rs0 = rsqrt_f64(bad0 ? 1e-300 : piv0);
-    double l0[8];
-#pragma unroll
-    for (int ia = CB; ia < 8; ++ia) l0[ia] = a[ia][CB] * rs0;               // meaningful in half 0
-    l0[CB] = (ty < cr) ? 0.0 : l0[CB];
-    // column c applied to column c + 1 inside the warp
-    const double lc1 = __shfl_sync(0xffffffffu, l0[CB], cr + 1);           // L(c+1, c)
-    double v[8];
-#pragma unroll
-    for (int ia = CB; ia < 8; ++ia) v[ia] = __shfl_sync(0xffffffffu, l0[ia], ty);   // same row, half 0
-    double a1[8];
-#pragma unroll
-    for (int ia = CB; ia < 8; ++ia) a1[ia] = fma(-v[ia], lc1, a[ia][CB]);   // meaningful in half 1
-    const double piv1 = __shfl_sync(0xffffffffu, a1[CB], 16 + cr + 1);     // half 1, ty == cr + 1
-    const bool bad1 = !(piv1 > 0.0);
-    const double rs1 = rsqrt_f64(bad1 ? 1e-300 : piv1);
+    const bool bad1 = !(d > 0.0);
+    const double p0 = bad0 ? 1e-300 : piv0;
+    const double rs0 = rsqrt_f64(p0);
+    const double rd = rsqrt_f64(bad1 ? 1e-300 : d);
+    const double rs1 = rd * (p0 * rs0);        // rsqrt(piv1)
+    const double w = a10 * rs0 * rs0;          // L(c+1, c) / L(c, c)
     const int slot = (c >> 1) & 3;
 #pragma unroll
     for (int ia = 0; ia < 8; ++ia) {
         double l = 0.0;
-        if (ia >= CB) l = half ? a1[ia] * rs1 : l0[ia];
-        if (ia == CB && half && ty < cr + 1) l = 0.0;
+        if (ia >= CB) l = half ? fma(-u[ia], w, a[ia][CB]) * rs1 : a[ia][CB] * rs0;
+        if (ia == CB && ty < cr + half) l = 0.0;          // rows above the diagonal
         sh.col[slot][half][ty + 16 * ia] = l;
     }
+    if (lane == 0) { sh.rs[c] = rs0; sh.rs[c + 1] = rs1; }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&sh.full[slot]));
-    // off the chain: bookkeeping
-    if (lane == cr) { sh.rinv[c] = (float)rs0; if (bad0) atomicExch(o.info, c + 1); }
-    if (lane == 16 + cr + 1) { sh.rinv[c + 1] = (float)rs1; if (bad1) atomicExch(o.info, c + 2); }
-#ifdef LB_CHOL_TRACE
-    if (lane == 0) { sh.t_pub[c] = clock64(); sh.t_emit[c] = clock64() - te0; }
-#endif
+    if (lane == 0 && (bad0 || bad1)) atomicExch(o.info, c + (bad0 ? 1 : 2));   // off the chain
 }
 
 template <int CB>
@@ -296,16 +283,10 @@ __device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, i
         const int c = CB * 16 + cr;            // pair (c, c+1) to derive; pair (c-2, c-1) to apply
         const int ps = ((c >> 1) - 1) & 3;     // ring slot of the previous pair
         const int owner = cr >> 1;
-#ifdef LB_CHOL_TRACE
-        const long long tw0 = clock64();
-#endif
         // the owner makes sure its ring slot is free (readers of pair c/2 - 4 are done) while it
         // would be waiting for the previous pair anyway
         if (warp == owner && c >= 8) mbar_wait(smem_u32(&sh.empty[(c >> 1) & 3]), ((c >> 3) & 1) ^ 1u);
         mbar_wait(smem_u32(&sh.full[ps]), (((c >> 1) - 1) >> 2) & 1u);     // previous pair published
-#ifdef LB_CHOL_TRACE
-        const long long tw1 = clock64();
-#endif
         double ci0[8], ci1[8], cj0[8], cj1[8];
 #pragma unroll
         for (int q = CB; q < 8; ++q) {
@@ -318,15 +299,7 @@ __device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, i
 #pragma unroll
         for (int ia = CB; ia < 8; ++ia)
             a[ia][CB] = fma(-ci1[ia], cj1[CB], fma(-ci0[ia], cj0[CB], a[ia][CB]));
-        if (warp == owner) {
-            chol_emit_pair<CB>(a, c, ty, lane, sh, o);
-        } else {
-            const int rel = (warp - owner - 1) & 7;                 // 0..6 among the other warps
-            if (rel < 4) {
-                chol_output_column(c - 2, rel * 32 + lane, sh.col[ps][0], o);
-                chol_output_column(c - 1, rel * 32 + lane, sh.col[ps][1], o);
-            }
-        }
+        if (warp == owner) chol_emit_pair<CB>(a, c, ty, lane, sh, o);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sh.empty[ps]));        // done reading the previous pair
         // rest of the rank-2 update
@@ -335,41 +308,64 @@ __device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, i
 #pragma unroll
             for (int ia = jb; ia < 8; ++ia)
                 a[ia][jb] = fma(-ci1[ia], cj1[jb], fma(-ci0[ia], cj0[jb], a[ia][jb]));
-#ifdef LB_CHOL_TRACE
-        if (lane == 0) { sh.t_wait[warp][c] = tw1 - tw0; sh.t_iter[warp][c] = clock64() - tw0; }
-#endif
-        if ((c & 31) == 0) {
-            // block-row (c/32 - 1) of R is complete once column c-1 has been written out
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                const int b = (c >> 5) - 1;
-                o.fac->rinv[b * 32 + threadIdx.x] = sh.rinv[b * 32 + threadIdx.x];
-                __threadfence();
-                __syncwarp();
-                if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&o.fac->flag[b]) = 1;
+    }
+}
+
+// The output warp: column k of L = row k of R -> caller's R (strictly lower part written as zero),
+// the 32 x 32 factor blocks (columns permuted for the apply kernel), 1/diag; raises flag[b] when
+// block-row b is complete.  Lane l handles the rows i = l + 32 j.
+__device__ __forceinline__ void chol_output_warp(int lane, CholShared& sh, const CholOut& o) {
+    const int pl = perm32(lane);
+#pragma unroll 1
+    for (int s = 0; s < PW / 2; ++s) {
+        const int slot = s & 3;
+        mbar_wait(smem_u32(&sh.full[slot]), (s >> 2) & 1u);
+#pragma unroll
+        for (int hcol = 0; hcol < 2; ++hcol) {
+            const int k = 2 * s + hcol, rb = k >> 5, rr = k & 31;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = lane + 32 * j;
+                const float l = i < k ? 0.f : (float)sh.col[slot][hcol][i];
+                o.R[k + (long)i * o.ldr] = l;                       // R(k, i) = L(i, k)
+                if (i >= k) {
+                    if (j == rb) o.fac->Rdiag[rb][rr][pl] = l;
+                    else o.fac->Roff[off_index(rb, j)][rr][pl] = l;
+                }
             }
+        }
+        if (lane < 2) o.fac->rinv[2 * s + lane] = (float)sh.rs[2 * s + lane];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sh.empty[slot]));
+        if ((s & 15) == 15) {                  // columns 32 b .. 32 b + 31 are out: publish block-row b
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile int*>(&o.fac->flag[s >> 4]) = 1;
         }
     }
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(CHOL_THREADS, 1)
 chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
                PanelFactors* __restrict__ fac, int* __restrict__ info) {
     __shared__ CholShared sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = 2 * warp + (lane >> 4);      // column residue
+    const int tx = 2 * warp + (lane >> 4);      // column residue (compute warps)
     const int ty = lane & 15;                   // row residue
     const CholOut o{R, ldr, fac, info};
-
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&sh.full[s]), 1); mbar_init(smem_u32(&sh.empty[s]), 8); }
+        for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&sh.full[s]), 1); mbar_init(smem_u32(&sh.empty[s]), 9); }
         fence_barrier_init();
     }
     pdl_wait();      // G and the cleared flags come from the reduce kernel
     // Only now may the dependent apply grid start: it synchronises on fac->flag[] (not on the
     // completion of this grid), so the flags must already have been cleared by the reduce kernel.
     pdl_trigger();
+    __syncthreads();
+    if (warp == 8) {
+        chol_output_warp(lane, sh, o);
+        return;
+    }
     double a[8][8];
 #pragma unroll
     for (int ia = 0; ia < 8; ++ia)
@@ -378,7 +374,6 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
             const int i = ty + 16 * ia, j = tx + 16 * jb;
             a[ia][jb] = (ia >= jb && i >= j) ? gram_elem(G, i, j) : 0.0;
         }
-    __syncthreads();
     if (warp == 0) chol_emit_pair<0>(a, 0, ty, lane, sh, o);   // columns 0, 1 need no update
     chol_block_column<0>(a, warp, tx, ty, lane, sh, o);
     chol_block_column<1>(a, warp, tx, ty, lane, sh, o);
@@ -388,37 +383,6 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
     chol_block_column<5>(a, warp, tx, ty, lane, sh, o);
     chol_block_column<6>(a, warp, tx, ty, lane, sh, o);
     chol_block_column<7>(a, warp, tx, ty, lane, sh, o);
-    // last pair and last block-row
-    constexpr int LS = ((PW >> 1) - 1) & 3;
-    mbar_wait(smem_u32(&sh.full[LS]), (((PW >> 1) - 1) >> 2) & 1u);
-    if (threadIdx.x < PW) {
-        chol_output_column(PW - 2, threadIdx.x, sh.col[LS][0], o);
-        chol_output_column(PW - 1, threadIdx.x, sh.col[LS][1], o);
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        fac->rinv[96 + threadIdx.x] = sh.rinv[96 + threadIdx.x];
-        __threadfence();
-        __syncwarp();
-        if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&fac->flag[3]) = 1;
-    }
-#ifdef LB_CHOL_TRACE
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int cb = 0; cb < 8; ++cb) {
-            long long dp = 0, em = 0, w[8] = {0}, it[8] = {0};
-            int n = 0;
-            for (int c = cb * 16 + (cb == 0 ? 4 : 0); c < cb * 16 + 16; c += 2) {
-                dp += sh.t_pub[c] - sh.t_pub[c - 2]; em += sh.t_emit[c]; ++n;
-                for (int q = 0; q < 8; ++q) { w[q] += sh.t_wait[q][c]; it[q] += sh.t_iter[q][c]; }
-            }
-            printf("CB %d: pair pub-to-pub %lld  emit %lld | wait/iter per warp:", cb, dp / n, em / n);
-            for (int q = 0; q < 8; ++q) printf(" %lld/%lld", w[q] / n, it[q] / n);
-            printf("\n");
-        }
-    }
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -628,7 +592,7 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
                          (const float*)A, lda, m, part)) != cudaSuccess) return le;
     if ((le = launch_pdl(gram128_reduce_kernel, dim3((GRAM_ELEMS + 31) / 32), dim3(1024), 0, stream,
                          (const double*)part, ggrid, G, fac->flag)) != cudaSuccess) return le;
-    if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(256), 0, stream, (const double*)G, R, ldr, fac,
+    if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr, fac,
                          info)) != cudaSuccess) return le;
     // programmatic dependent launch: the apply grid may start while the Cholesky grid is running
     cudaLaunchConfig_t cfg{};

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -87,8 +88,12 @@ struct Workspace {
 };
 
 int gram_bn(int h) { return h >= 512 ? 256 : 128; }
-// update: HBM-bound levels (K = h <= 1024) take the BN=128 variant (deeper C ring), the rest BN=256
-int update_bn(int h) { return h >= 2048 ? 256 : 128; }
+// update kernel per level, from a sweep on B200 at m = 16384 (scripts/gpu_upd_variants.py):
+//   h <= 2048 : TMA-streamed C, BN = 128 (4-slot C ring)      75 / 183 us at h = 1024 / 2048
+//   h  = 4096 : per-thread epilogue, BN = 256 (all smem to the A/B ring)            462 us
+//   h >= 8192 : TMA-streamed C, BN = 256                                            1.60 ms
+int update_bn(int h) { return h >= 4096 ? 256 : 128; }
+bool update_uses_tma(int h) { return h < 4096 || h >= 8192; }
 
 Workspace plan_workspace(int num_sms, int m, int n) {
     Workspace w{};
@@ -150,10 +155,10 @@ struct Recursion {
         HalfMatrix rm{p->R12h, h, h, h};
         const int ubn = update_bn(h);
         check(make_tensor_map_f16(&r12map, rm, 64, ubn));
-        if (p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
+        if (update_uses_tma(h) && p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
             check(tc_update_tma(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, h, p->A, p->m,
                                 p->n, p->lda, c0 + h, p->Qh, p->ldh, true));
-        } else {   // TMA needs 16-byte aligned column strides: per-thread epilogue otherwise
+        } else {   // (TMA also needs 16-byte aligned column strides)
             check(tc_update(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, h,
                             p->A + (long)(c0 + h) * p->lda, p->lda, p->Qh + (long)(c0 + h) * p->ldh,
                             p->ldh, true));
@@ -577,7 +582,11 @@ int later_b200_gemm_update(later_b200_ctx* ctx, const void* Qh, int q_rows, int 
     if (!ctx || !Qh || !Bh || !C) return LATER_B200_EINVAL;
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
-    const int bn = (Nc >= 256 && K >= 2048) ? 256 : 128;
+    int bn = (Nc >= 256 && K >= 2048) ? 256 : 128;
+    int variant = 0;
+    if (const char* v = getenv("LB_UPDATE_VARIANT")) variant = atoi(v);   // diagnostics only
+    if (variant == 1 || variant == 2) bn = Nc >= 256 ? 256 : 128;
+    if (variant == 3) bn = 128;
     CUtensorMap q64, bmap;
     HalfMatrix qm{static_cast<const __half*>(Qh), q_rows, q_cols, ldq};
     HalfMatrix bm{static_cast<const __half*>(Bh), K, Nc, ldb};
@@ -588,7 +597,7 @@ int later_b200_gemm_update(later_b200_ctx* ctx, const void* Qh, int q_rows, int 
                         (subtract == 0 ? Ch == nullptr
                                        : (Ch && ldch % 8 == 0 && (reinterpret_cast<uintptr_t>(Ch) & 15) == 0)) &&
                         Nc % bn == 0;
-    if (tma_ok)
+    if (tma_ok && variant != 1)
         e = tc_update_tma(ctx->stream, ctx->num_sms, q64, bmap, bn, 0, q_rows, colA, K, 0, Nc, C, q_rows,
                           Nc, ldc, 0, static_cast<__half*>(Ch), ldch, subtract != 0);
     else

@@ -115,7 +115,8 @@ def test_panel_vs_oracle(qr, ctx, m, dist):
 
 # ------------------------------------------------------------------------------ RGSQRF vs oracle
 @pytest.mark.parametrize("m,n,dist", [(256, 256, "normal"), (512, 256, "normal"), (1024, 512, "uniform"),
-                                      (1024, 1024, "uniform"), (2048, 1024, "normal"), (800, 128, "normal")])
+                                      (1024, 1024, "uniform"), (2048, 1024, "normal"), (800, 128, "normal"),
+                                      (1000, 256, "normal")])
 def test_rgsqrf_vs_oracle(qr, ctx, m, n, dist):
     rng = np.random.default_rng(1000 + m + n)
     A0 = rng.random((m, n), dtype=np.float32) if dist == "uniform" else rng.standard_normal((m, n), dtype=np.float32)
