@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace lb {
@@ -247,6 +248,190 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant of the Gram product for the large (compute-bound) levels: a cluster of two
+// CTAs computes a 256 x 256 tile with tcgen05.mma.cta_group::2 (M = 256).  Each CTA stages its own
+// 128 rows of A and HALF of the B tile, so per SM the shared-memory fill traffic drops from 48 to
+// 32 KiB per k-block (and the ring gets 6 stages instead of 4); the accumulator rows 0-127 live in
+// the leader's TMEM, rows 128-255 in the peer's.  Protocol:
+//   full[s]   leader's barrier; the leader arms it for the bytes of BOTH CTAs, the peer's TMA
+//             (cp.async.bulk.tensor ... cta_group::2) credits it through its shared::cluster address
+//   empty[s]  one per CTA; tcgen05.commit.cta_group::2 ... multicast arrives on both
+//   tfull[a]  one per CTA (multicast commit); tempty[a] leader's, 4 local + 4 remote arrivals
+template <int BN>
+struct Cfg2 {
+    static constexpr int STAGES = 6;
+    static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;      // per CTA
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gram2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const TcGemmParams p) {
+    using C = Cfg2<BN>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&mapA);
+        prefetch_tensormap(&mapB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc_2cta(tmem_slot, C::TMEM_COLS);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before_sync();
+    cluster_sync();                                    // barriers of both CTAs are initialised
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_trigger();
+    pdl_wait();
+
+    const int pairs_m = p.tiles_m >> 1;
+    const int items = pairs_m * p.tiles_n;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = cluster_id; item < items; item += num_clusters) {
+                int pm, n_blk;
+                tile_coords(item, pairs_m, p.tiles_n, pm, n_blk);
+                const int m_blk = 2 * pm + (int)rank;
+                for (int kb = 0; kb < p.kb_total; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + A_TILE_BYTES;
+                    const uint32_t lead_full = mapa(full_bar(stage), 0);
+                    if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                    tma_load_2d_2cta(a_dst, &mapA, lead_full, p.a_c0 + kb * BK, p.a_c1 + m_blk * BM);
+                    tma_load_2d_2cta(b_dst, &mapB, lead_full, p.b_c0 + kb * BK,
+                                     p.b_c1 + n_blk * BN + (int)rank * (BN / 2));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader only)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc(0, 0u, 0u, 2 * BM, BN);   // M = 256
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int item = cluster_id; item < items; item += num_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.kb_total; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after_sync();
+                    const uint32_t a_src = smem_base + stage * C::STAGE_BYTES;
+                    const uint64_t a_desc = make_smem_desc_sw128(a_src, 16, 1024);
+                    const uint64_t b_desc = make_smem_desc_sw128(a_src + A_TILE_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_f16_2cta(d_tmem, a_desc + k * (UMMA_K * 2 / 16), b_desc + k * (UMMA_K * 2 / 16),
+                                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2cta(empty_bar(stage), 3);   // frees the slot in both CTAs
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_2cta(tfull_bar(acc), 3);         // accumulator complete, both CTAs
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (both CTAs)
+        const int quad = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = cluster_id; item < items; item += num_clusters) {
+            int pm, n_blk;
+            tile_coords(item, pairs_m, p.tiles_n, pm, n_blk);
+            const int row = (2 * pm + (int)rank) * BM + quad * 32 + lane;
+            const bool row_ok = row < p.M;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after_sync();
+            const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n_blk * BN + c * 32;
+                uint32_t d[32];
+                tmem_ld_32x32(t_addr + c * 32, d);
+                tmem_ld_wait();
+                float* cp = p.C + row + (long)col0 * p.ldc;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (row_ok && col0 + j < p.N) {
+                        const float v = __uint_as_float(d[j]);
+                        cp[(long)j * p.ldc] = v;
+                        if (p.Ch) p.Ch[row + (long)(col0 + j) * p.ldch] = __float2half_rn(v);
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(acc), 0));   // leader's barrier
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before_sync();
+    cluster_sync();          // nobody tears down while the partner may still touch its smem / TMEM
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
+    }
+}
+
+template <int BN>
+cudaError_t launch_gram2(cudaStream_t stream, int num_sms, const CUtensorMap& mapA,
+                         const CUtensorMap& mapB, const TcGemmParams& p) {
+    const int items = (p.tiles_m / 2) * p.tiles_n;
+    const int clusters = std::max(1, std::min(items, num_sms / 2));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg2<BN>::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gram2_kernel<BN>, mapA, mapB, p);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
                                      float* __restrict__ C, long ldc, __half* __restrict__ Ch,
                                      long ldch) {
@@ -312,6 +497,9 @@ cudaError_t tc_gemm_init() {
     LB_SET(128, true, EPI_STORE) LB_SET(256, true, EPI_STORE)
     LB_SET(128, false, EPI_ADD) LB_SET(256, false, EPI_ADD)
 #undef LB_SET
+    if ((e = cudaFuncSetAttribute(tc_gram2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg2<256>::SMEM_BYTES)) != cudaSuccess)
+        return e;
     return cudaSuccess;
 }
 
@@ -409,6 +597,15 @@ cudaError_t tc_gram(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_12
     p.b_c0 = row0; p.b_c1 = colB;
     p.C = C; p.ldc = ldc; p.Ch = Ch; p.ldch = ldch; p.part = part;
     cudaError_t e;
+    static const bool use_pair = [] { const char* v = getenv("LB_GRAM_2CTA"); return !v || atoi(v) != 0; }();
+    const int ntiles = p.tiles_m * p.tiles_n;
+    if (p.splits == 1 && bn == 256 && use_pair && p.tiles_m % 2 == 0 && ntiles >= 2 * num_sms &&
+        ntiles <= 1024) {
+        // mid-size level (measured on B200, m = 16384: h = 4096 412 us vs 438 us single-CTA; at
+        // h = 8192 both variants sit at the power-capped tensor peak, 1.36-1.38 PFLOP/s):
+        // CTA-pair kernel; its B map is the 128-row box (half of the 256-wide tile)
+        return launch_gram2<256>(stream, num_sms, mapQ_128, mapQ_128, p);
+    }
     if (p.splits == 1) {
         e = (bn == 256) ? launch<256, false, EPI_STORE>(stream, num_sms, mapQ_128, mapQ_bn, p)
                         : launch<128, false, EPI_STORE>(stream, num_sms, mapQ_128, mapQ_bn, p);
