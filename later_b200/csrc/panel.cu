@@ -214,20 +214,26 @@ __device__ __forceinline__ double rsqrt_f64(double x) {
     return fma(0.5 * y, e, y);                 // one Newton step: ~2^-45 relative
 }
 
-// R = chol(G)^T in fp64, one CTA: 8 compute warps + 1 output warp.
+// R = chol(G)^T in fp64, one CTA: 8 compute warps + 4 output warps.
 // Compute thread (tx = column residue mod 16, ty = row residue mod 16) keeps the elements
 // (i, j) = (ty + 16 ia, tx + 16 jb), ia >= jb, of the trailing lower triangle in registers (36
 // doubles).  Warp w holds tx in {2w, 2w + 1} (one per half-warp): an even column c and its right
 // neighbour c + 1 live in the same warp, which derives BOTH with shuffles only.  Column pairs travel
-// through a 4-slot shared-memory ring guarded by mbarriers and are applied by every compute warp as
-// rank-2 updates; the ninth warp does nothing but write finished columns (rows of R, the 32x32
+// through an 8-slot shared-memory ring (published-pair counter with release/acquire semantics for
+// "full", mbarriers for "empty") and are applied by every compute warp as
+// rank-2 updates; four more warps do nothing but write finished columns (rows of R, the 32x32
 // factor blocks, 1/diag, the block-row flags) to global memory, so no compute warp ever leaves the
 // register/shared-memory domain and nobody waits at a block-wide barrier.
+constexpr int CHOL_RING = 8;            // ring slots (column pairs in flight)
+
 struct CholShared {
-    double col[4][2][PW];
+    double col[CHOL_RING][2][PW];
     double rs[PW];              // 1 / L(c, c), written by the owner before it publishes column c
-    uint64_t full[4];
-    uint64_t empty[4];
+    uint64_t empty[CHOL_RING];  // mbarriers: all readers of a slot are done
+    int published;              // number of column pairs published so far (release / acquire)
+#ifdef LB_CHOL_TRACE
+    long long tr[64][8];        // per pair: owner timestamps
+#endif
 };
 
 struct CholOut {
@@ -236,7 +242,23 @@ struct CholOut {
     int* info;
 };
 
-constexpr int CHOL_THREADS = 9 * 32;
+__device__ __forceinline__ void chol_publish(int* counter, int value) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(counter)), "r"(value) : "memory");
+}
+// Spin until `value` pairs have been published.  A plain acquire load is polled instead of an
+// mbarrier: waking up from mbarrier.try_wait costs ~160 cycles on the serial chain, a shared-memory
+// load ~30.
+__device__ __forceinline__ void chol_wait_published(const int* counter, int value) {
+    int v;
+    unsigned long long n = 0;
+    do {
+        asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(counter)) : "memory");
+        if (++n > (unsigned long long)(LB_SPIN_LIMIT)) __trap();   // protocol bug: fail, do not hang
+    } while (v < value);
+}
+
+constexpr int CHOL_OUT_WARPS = 4;                 // output warp j writes rows 32 j .. 32 j + 31
+constexpr int CHOL_THREADS = (8 + CHOL_OUT_WARPS) * 32;
 
 // Derives columns c (even) and c + 1 and publishes the pair.  This is the serial chain of the
 // factorisation, so the two reciprocal square roots are made independent of each other:
@@ -261,7 +283,7 @@ __device__ __forceinline__ void chol_emit_pair(double (&a)[8][8], int c, int ty,
     const double rd = rsqrt_f64(bad1 ? 1e-300 : d);
     const double rs1 = rd * (p0 * rs0);        // rsqrt(piv1)
     const double w = a10 * rs0 * rs0;          // L(c+1, c) / L(c, c)
-    const int slot = (c >> 1) & 3;
+    const int slot = (c >> 1) & (CHOL_RING - 1);
 #pragma unroll
     for (int ia = 0; ia < 8; ++ia) {
         double l = 0.0;
@@ -271,7 +293,7 @@ __device__ __forceinline__ void chol_emit_pair(double (&a)[8][8], int c, int ty,
     }
     if (lane == 0) { sh.rs[c] = rs0; sh.rs[c + 1] = rs1; }
     __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&sh.full[slot]));
+    if (lane == 0) chol_publish(&sh.published, (c >> 1) + 1);
     if (lane == 0 && (bad0 || bad1)) atomicExch(o.info, c + (bad0 ? 1 : 2));   // off the chain
 }
 
@@ -281,12 +303,22 @@ __device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, i
 #pragma unroll 1
     for (int cr = (CB == 0 ? 2 : 0); cr < 16; cr += 2) {
         const int c = CB * 16 + cr;            // pair (c, c+1) to derive; pair (c-2, c-1) to apply
-        const int ps = ((c >> 1) - 1) & 3;     // ring slot of the previous pair
+        const int ps = ((c >> 1) - 1) & (CHOL_RING - 1);     // ring slot of the previous pair
         const int owner = cr >> 1;
         // the owner makes sure its ring slot is free (readers of pair c/2 - 4 are done) while it
         // would be waiting for the previous pair anyway
-        if (warp == owner && c >= 8) mbar_wait(smem_u32(&sh.empty[(c >> 1) & 3]), ((c >> 3) & 1) ^ 1u);
-        mbar_wait(smem_u32(&sh.full[ps]), (((c >> 1) - 1) >> 2) & 1u);     // previous pair published
+#ifdef LB_CHOL_TRACE
+        const long long t0 = clock64();
+#endif
+        if (warp == owner && c >= 2 * CHOL_RING)
+            mbar_wait(smem_u32(&sh.empty[(c >> 1) & (CHOL_RING - 1)]), (((c >> 1) / CHOL_RING) & 1) ^ 1u);
+#ifdef LB_CHOL_TRACE
+        const long long t1 = clock64();
+#endif
+        chol_wait_published(&sh.published, c >> 1);                  // previous pair published
+#ifdef LB_CHOL_TRACE
+        const long long t2 = clock64();
+#endif
         double ci0[8], ci1[8], cj0[8], cj1[8];
 #pragma unroll
         for (int q = CB; q < 8; ++q) {
@@ -299,7 +331,13 @@ __device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, i
 #pragma unroll
         for (int ia = CB; ia < 8; ++ia)
             a[ia][CB] = fma(-ci1[ia], cj1[CB], fma(-ci0[ia], cj0[CB], a[ia][CB]));
+#ifdef LB_CHOL_TRACE
+        const long long t3 = clock64();
+#endif
         if (warp == owner) chol_emit_pair<CB>(a, c, ty, lane, sh, o);
+#ifdef LB_CHOL_TRACE
+        const long long t4 = clock64();
+#endif
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sh.empty[ps]));        // done reading the previous pair
         // rest of the rank-2 update
@@ -308,39 +346,43 @@ __device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, i
 #pragma unroll
             for (int ia = jb; ia < 8; ++ia)
                 a[ia][jb] = fma(-ci1[ia], cj1[jb], fma(-ci0[ia], cj0[jb], a[ia][jb]));
+#ifdef LB_CHOL_TRACE
+        if (warp == owner && lane == 0) {
+            long long* r = sh.tr[c >> 1];
+            r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3; r[4] = t4; r[5] = clock64();
+        }
+#endif
     }
 }
 
-// The output warp: column k of L = row k of R -> caller's R (strictly lower part written as zero),
-// the 32 x 32 factor blocks (columns permuted for the apply kernel), 1/diag; raises flag[b] when
-// block-row b is complete.  Lane l handles the rows i = l + 32 j.
-__device__ __forceinline__ void chol_output_warp(int lane, CholShared& sh, const CholOut& o) {
+// The output warps: column k of L = row k of R -> caller's R (strictly lower part written as zero),
+// the 32 x 32 factor blocks (columns permuted for the apply kernel), 1/diag; output warp j owns the
+// rows i = 32 j + lane; warp 0 also raises flag[b] when block-row b is complete (after a named
+// barrier among the output warps, so that all of their global writes precede the flag).
+__device__ __forceinline__ void chol_output_warp(int j, int lane, CholShared& sh, const CholOut& o) {
     const int pl = perm32(lane);
+    const int i = lane + 32 * j;
 #pragma unroll 1
     for (int s = 0; s < PW / 2; ++s) {
-        const int slot = s & 3;
-        mbar_wait(smem_u32(&sh.full[slot]), (s >> 2) & 1u);
+        const int slot = s & (CHOL_RING - 1);
+        chol_wait_published(&sh.published, s + 1);
 #pragma unroll
         for (int hcol = 0; hcol < 2; ++hcol) {
             const int k = 2 * s + hcol, rb = k >> 5, rr = k & 31;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = lane + 32 * j;
-                const float l = i < k ? 0.f : (float)sh.col[slot][hcol][i];
-                o.R[k + (long)i * o.ldr] = l;                       // R(k, i) = L(i, k)
-                if (i >= k) {
-                    if (j == rb) o.fac->Rdiag[rb][rr][pl] = l;
-                    else o.fac->Roff[off_index(rb, j)][rr][pl] = l;
-                }
+            const float l = i < k ? 0.f : (float)sh.col[slot][hcol][i];
+            o.R[k + (long)i * o.ldr] = l;                           // R(k, i) = L(i, k)
+            if (i >= k) {
+                if (j == rb) o.fac->Rdiag[rb][rr][pl] = l;
+                else o.fac->Roff[off_index(rb, j)][rr][pl] = l;
             }
         }
-        if (lane < 2) o.fac->rinv[2 * s + lane] = (float)sh.rs[2 * s + lane];
+        if (j == 0 && lane < 2) o.fac->rinv[2 * s + lane] = (float)sh.rs[2 * s + lane];
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sh.empty[slot]));
         if ((s & 15) == 15) {                  // columns 32 b .. 32 b + 31 are out: publish block-row b
             __threadfence();
-            __syncwarp();
-            if (lane == 0) *reinterpret_cast<volatile int*>(&o.fac->flag[s >> 4]) = 1;
+            asm volatile("bar.sync 3, %0;" ::"n"(CHOL_OUT_WARPS * 32) : "memory");
+            if (j == 0 && lane == 0) *reinterpret_cast<volatile int*>(&o.fac->flag[s >> 4]) = 1;
         }
     }
 }
@@ -354,7 +396,8 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
     const int ty = lane & 15;                   // row residue
     const CholOut o{R, ldr, fac, info};
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&sh.full[s]), 1); mbar_init(smem_u32(&sh.empty[s]), 9); }
+        for (int s = 0; s < CHOL_RING; ++s) mbar_init(smem_u32(&sh.empty[s]), 8 + CHOL_OUT_WARPS);
+        sh.published = 0;
         fence_barrier_init();
     }
     pdl_wait();      // G and the cleared flags come from the reduce kernel
@@ -362,8 +405,8 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
     // completion of this grid), so the flags must already have been cleared by the reduce kernel.
     pdl_trigger();
     __syncthreads();
-    if (warp == 8) {
-        chol_output_warp(lane, sh, o);
+    if (warp >= 8) {
+        chol_output_warp(warp - 8, lane, sh, o);
         return;
     }
     double a[8][8];
@@ -383,6 +426,21 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
     chol_block_column<5>(a, warp, tx, ty, lane, sh, o);
     chol_block_column<6>(a, warp, tx, ty, lane, sh, o);
     chol_block_column<7>(a, warp, tx, ty, lane, sh, o);
+#ifdef LB_CHOL_TRACE
+    asm volatile("bar.sync 2, 256;");
+    if (threadIdx.x == 0) {
+        for (int cb = 0; cb < 8; ++cb) {
+            long long e = 0, f = 0, l = 0, em = 0, rest = 0, per = 0; int n = 0;
+            for (int sidx = cb * 8 + (cb == 0 ? 2 : 0); sidx < cb * 8 + 8; ++sidx) {
+                const long long* r = sh.tr[sidx];
+                e += r[1] - r[0]; f += r[2] - r[1]; l += r[3] - r[2]; em += r[4] - r[3]; rest += r[5] - r[4];
+                per += r[4] - sh.tr[sidx - 1][4]; ++n;
+            }
+            printf("CB %d owner: empty-wait %lld full-wait %lld lds+blockcol %lld emit %lld rest %lld | emit-to-emit %lld\n",
+                   cb, e / n, f / n, l / n, em / n, rest / n, per / n);
+        }
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
