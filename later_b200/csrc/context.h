@@ -38,6 +38,7 @@ struct later_b200_ctx {
         cudaGraphExec_t exec = nullptr;
         Plan plan;
         long launches = 0;
+        bool seen = false;      // plan was launched directly once; capture on the next identical call
     } graphs[3];
 
     // pipelined host path: copy streams and events

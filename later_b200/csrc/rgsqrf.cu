@@ -265,6 +265,17 @@ int run_stage(later_b200_ctx* ctx, int stage) {
         return rc;
     }
     auto& slot = ctx->graphs[stage];
+    // A plan seen for the first time is launched directly: capturing and instantiating a graph of
+    // ~900 nodes costs tens of milliseconds, which only pays off from the second identical call on
+    // (the reference's driver, test/test_qr.cu, calls the factorisation exactly once per process).
+    if (!slot.exec && !(slot.seen && same_plan(slot.plan, ctx->plan))) {
+        long l = 0;
+        int rc = enqueue_stage(ctx, stage, &l);
+        ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + l;
+        slot.plan = ctx->plan;
+        slot.seen = true;
+        return rc;
+    }
     if (slot.exec && same_plan(slot.plan, ctx->plan)) {
         e = cudaGraphLaunch(slot.exec, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
@@ -274,6 +285,14 @@ int run_stage(later_b200_ctx* ctx, int stage) {
     if (slot.exec) {
         cudaGraphExecDestroy(slot.exec);
         slot.exec = nullptr;
+        if (!same_plan(slot.plan, ctx->plan)) {   // a different problem: start over with a direct launch
+            long l = 0;
+            int rc = enqueue_stage(ctx, stage, &l);
+            ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + l;
+            slot.plan = ctx->plan;
+            slot.seen = true;
+            return rc;
+        }
     }
     // Capture on a private stream so the legacy default stream can be the context's stream.
     cudaStream_t cap = nullptr;
