@@ -72,16 +72,6 @@ __global__ void cast_shadow_kernel(const float* __restrict__ A, long lda, int m,
     }
 }
 
-// Strictly lower triangle of R := 0 (the algorithm never produces it; the reference leaves it
-// untouched and relies on a fresh cudaMalloc, test/test_qr.cu:49-50).
-__global__ void zero_lower_kernel(float* __restrict__ R, long ldr, int n) {
-    pdl_trigger();
-    pdl_wait();
-    const int j = blockIdx.y;
-    for (int i = j + 1 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        R[i + (long)j * ldr] = 0.f;
-}
-
 struct Workspace {
     size_t qh_bytes, r12h_bytes, wh_bytes, part_bytes, panel_bytes, total;
     long ldh;
@@ -147,8 +137,10 @@ struct Recursion {
         float* R12 = p->R + c0 + (long)(c0 + h) * p->ldr;
         // R12 = Q1^T A2 (fp32 into R, fp16 copy for the update)
         const int splits = choose_gram_splits(ctx->num_sms, h, h, bn, p->m);
+        // (the mirror block R21, which the algorithm never produces, is written as zero on the way)
         check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, c0 + h, h,
-                      R12, p->ldr, p->R12h, h, p->part, splits));
+                      R12, p->ldr, p->R12h, h, p->part, splits,
+                      p->R + (c0 + h) + (long)c0 * p->ldr));
         launches += splits > 1 ? 2 : 1;
         // A2 -= Q1 R12, refreshing A2's fp16 shadow
         CUtensorMap r12map;
@@ -230,13 +222,6 @@ int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
         if ((e = launch_pdl(cast_shadow_kernel, grid, dim3(256), 0, ctx->stream, (const float*)p.A,
                             (long)p.lda, p.m, cast_lo, cast_hi, p.Qh, p.ldh, vec_ok)) != cudaSuccess)
             return cuda_fail(ctx, e, "cast launch");
-        rec.launches += 1;
-    }
-    if (stage != STAGE_REST && p.n > NMIN) {
-        dim3 zgrid((unsigned)std::min(8, (p.n + 255) / 256), (unsigned)p.n);
-        if ((e = launch_pdl(zero_lower_kernel, zgrid, dim3(256), 0, ctx->stream, p.R, (long)p.ldr,
-                            p.n)) != cudaSuccess)
-            return cuda_fail(ctx, e, "zero launch");
         rec.launches += 1;
     }
     if (stage == STAGE_ALL) rec.qr(0, p.n);

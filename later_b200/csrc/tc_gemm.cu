@@ -222,6 +222,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             const float v = __uint_as_float(d[j]) * dsc;
                             cp[(long)j * p.ldc] = v;
                             if (p.Ch) p.Ch[row + (long)(col0 + j) * p.ldch] = __float2half_rn(v);
+                            if (p.Z) p.Z[row + (long)(col0 + j) * p.ldc] = 0.f;
                         }
                     }
                 } else {  // EPI_PARTIAL
@@ -393,6 +394,7 @@ tc_gram2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         const float v = __uint_as_float(d[j]);
                         cp[(long)j * p.ldc] = v;
                         if (p.Ch) p.Ch[row + (long)(col0 + j) * p.ldch] = __float2half_rn(v);
+                        if (p.Z) p.Z[row + (long)(col0 + j) * p.ldc] = 0.f;
                     }
                 }
             }
@@ -434,7 +436,7 @@ cudaError_t launch_gram2(cudaStream_t stream, int num_sms, const CUtensorMap& ma
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
                                      float* __restrict__ C, long ldc, __half* __restrict__ Ch,
-                                     long ldch) {
+                                     long ldch, float* __restrict__ Z) {
     const long total = (long)M * N;
     pdl_trigger();
     pdl_wait();
@@ -446,6 +448,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
         const int j = (int)(idx / M);
         C[i + (long)j * ldc] = s;
         if (Ch) Ch[i + (long)j * ldch] = __float2half_rn(s);
+        if (Z) Z[i + (long)j * ldc] = 0.f;
     }
 }
 
@@ -583,7 +586,7 @@ int choose_gram_splits(int num_sms, int Mc, int Nc, int bn, int k_rows) {
 cudaError_t tc_gram(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128,
                     const CUtensorMap& mapQ_bn, int bn, int row0, int k_rows, int colA, int Mc,
                     int colB, int Nc, float* C, long ldc, __half* Ch, long ldch, float* part,
-                    int splits) {
+                    int splits, float* Z) {
     TcGemmParams p{};
     p.M = Mc;
     p.N = Nc;
@@ -596,6 +599,7 @@ cudaError_t tc_gram(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_12
     p.a_c0 = row0; p.a_c1 = colA;
     p.b_c0 = row0; p.b_c1 = colB;
     p.C = C; p.ldc = ldc; p.Ch = Ch; p.ldch = ldch; p.part = part;
+    p.Z = p.splits == 1 ? Z : nullptr;      // with split-K the reduce kernel does the zeroing
     cudaError_t e;
     static const bool use_pair = [] { const char* v = getenv("LB_GRAM_2CTA"); return !v || atoi(v) != 0; }();
     const int ntiles = p.tiles_m * p.tiles_n;
@@ -615,7 +619,7 @@ cudaError_t tc_gram(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_12
     e = (bn == 256) ? launch<256, false, EPI_PARTIAL>(stream, num_sms, mapQ_128, mapQ_bn, p)
                     : launch<128, false, EPI_PARTIAL>(stream, num_sms, mapQ_128, mapQ_bn, p);
     if (e != cudaSuccess) return e;
-    return splitk_reduce(stream, part, p.splits, Mc, Nc, C, ldc, Ch, ldch);
+    return splitk_reduce(stream, part, p.splits, Mc, Nc, C, ldc, Ch, ldch, Z);
 }
 
 cudaError_t tc_update(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_64,
@@ -641,12 +645,12 @@ cudaError_t tc_update(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_
 }
 
 cudaError_t splitk_reduce(cudaStream_t stream, const float* part, int splits, int M, int N, float* C,
-                          long ldc, __half* Ch, long ldch) {
+                          long ldc, __half* Ch, long ldch, float* Z) {
     const long total = (long)M * N;
     const int threads = 256;
     const int blocks = (int)std::min<long>((total + threads - 1) / threads, 148L * 8);
     cudaError_t e = launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(threads), 0, stream, part, splits,
-                               M, N, C, ldc, Ch, ldch);
+                               M, N, C, ldc, Ch, ldch, Z);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -45,6 +45,8 @@ struct TcGemmParams {
     long ldch;
     float* part;            // split-K workspace: [splits][N][M]
     const float* dscale;    // optional device scalar multiplied into D before the epilogue op
+    float* Z;               // optional: a block of the same shape and ld as C that is set to zero
+                            // (R21 of the recursion node: never produced, must read as 0)
 };
 
 // Encodes a SWIZZLE_128B tiled tensor map over a column-major fp16 matrix with box
@@ -65,7 +67,7 @@ struct TcGemmPlan {
 cudaError_t tc_gram(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128,
                     const CUtensorMap& mapQ_bn, int bn, int row0, int k_rows, int colA, int Mc,
                     int colB, int Nc, float* C, long ldc, __half* Ch, long ldch, float* part,
-                    int splits);
+                    int splits, float* Z = nullptr);
 
 // C[Mr x Nc] (fp32, ld ldc) (-)= Qh(row0:row0+Mr, colA:colA+K) * Bh[K x Nc]; Bh is addressed through
 // its own tensor map with origin (0, colB0).  sub=true: C -= D; sub=false: C = D.  Optional fp16
@@ -85,7 +87,7 @@ void tc_fill_update(TcGemmParams& p, int bn, int row0, int Mr, int colA, int K, 
 
 // Sums split-K partials in a fixed order (deterministic) and writes C (+ fp16 copy).
 cudaError_t splitk_reduce(cudaStream_t stream, const float* part, int splits, int M, int N, float* C,
-                          long ldc, __half* Ch, long ldch);
+                          long ldc, __half* Ch, long ldch, float* Z = nullptr);
 
 // Picks split-K so that tiles*splits roughly fills the machine.
 int choose_gram_splits(int num_sms, int Mc, int Nc, int bn, int k_rows);
