@@ -46,11 +46,17 @@ size_t later_b200_workspace_bytes(const later_b200_ctx* ctx, int m, int n);
 /* Recursive Gram-Schmidt QR.  Replaces later_rgsqrf (reference include/LATER.h:39,
  * QR/later_rgsqrf.cu:62-79).  In: A (device, m x n, lda >= m).  Out: A <- explicit Q,
  * R <- upper-triangular factor (the whole strictly lower triangle is written as zero).
- * Requirements: m >= n, n a multiple of 128, m a multiple of 8. */
+ * Requirements: m >= n, n = 128 * 2^k (as in the reference), m a multiple of 8. */
 int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr);
 
-/* Same with HOST buffers: copies A to the device, factors, copies Q and R back (end-to-end path
- * used by bench.py's e2e figure). */
+/* Same with HOST buffers (what the reference's driver does by hand, test/test_qr.cu:47-56): A goes
+ * to the device in doubling column pieces, each left-spine node of the recursion starting as soon
+ * as its columns have arrived; every block of R and every max(128, n/16) columns of Q travel back
+ * the moment they are final, while the factorisation continues.  hA <- Q.  hR receives its block
+ * upper triangle at that granularity (strictly lower entries inside the diagonal blocks are
+ * written as zero); the blocks below are NOT written - they are zero by definition and the
+ * reference never writes them either.  Page-locked buffers are needed for the overlap (and for
+ * the copies to be cached as graph nodes); pageable ones work, serialised.  Blocks until done. */
 int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda, float* hR,
                            int ldr);
 

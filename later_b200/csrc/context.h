@@ -29,21 +29,25 @@ struct later_b200_ctx {
         float* part = nullptr; size_t part_floats = 0;
         void* panel_scratch = nullptr;
         unsigned long arena_gen = 0;
+        // host buffers of later_b200_rgsqrf_host (null for the device entry points): the copies are
+        // part of that call's graph, so they are part of its identity
+        float* hA = nullptr; long hlda = 0;
+        float* hR = nullptr; long hldr = 0;
         bool valid = false;
     } plan;
 
-    // Cached executable graphs: [0] whole factorisation, [1] left recursion, [2] the rest
-    // (the two halves are used by the pipelined host entry point).
+    // Cached executable graphs: [0] factorisation of a device matrix, [1] the host entry point
+    // (same launches with the PCIe copies woven in as memcpy nodes on forked branches).
     struct GraphSlot {
         cudaGraphExec_t exec = nullptr;
         Plan plan;
         long launches = 0;
         bool seen = false;      // plan was launched directly once; capture on the next identical call
-    } graphs[3];
+    } graphs[2];
 
-    // pipelined host path: copy streams and events
+    // pipelined host path: copy streams and a pool of fork/join events
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> events;
 
     // device staging buffers for the *_host entry point
     float* dA = nullptr; size_t dA_bytes = 0;

@@ -103,10 +103,106 @@ Workspace plan_workspace(int num_sms, int m, int n) {
     return w;
 }
 
+// The PCIe legs of later_b200_rgsqrf_host, woven into the recursion.  Column c of A is first read
+// by the node whose right half contains it, and only the left spine of the tree ever reads
+// columns nothing has updated yet - so the matrix is sent in doubling pieces [0,c) [c,2c) [2c,4c) ...
+// and each left-spine node waits for just the piece it is about to touch.  On the way out, an R12
+// block is final as soon as its Gram product is, and a block of Q columns (with the diagonal block
+// of R) as soon as its subtree is done; each goes back while the factorisation continues.
+// The copies run on two side streams forked from and joined back into the main stream, so the
+// same enqueue code works directly and inside a stream capture (where they become memcpy nodes).
+struct HostPipe {
+    later_b200_ctx* ctx = nullptr;
+    float* hA = nullptr; long hlda = 0;
+    float* hR = nullptr; long hldr = 0;
+    int m = 0, n = 0, chunk = NMIN;
+    float* dA = nullptr;       // device staging, column-major with leading dimensions m and n
+    float* dR = nullptr;
+    std::vector<int> in_end;   // right edge of each H2D piece
+    std::vector<cudaEvent_t> in_ev;
+    size_t used = 0;
+    cudaError_t err = cudaSuccess;
+
+    void check(cudaError_t e) {
+        if (err == cudaSuccess && e != cudaSuccess) err = e;
+    }
+    cudaEvent_t event() {
+        if (used == ctx->events.size()) {
+            cudaEvent_t ev = nullptr;
+            check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            if (!ev) return nullptr;
+            ctx->events.push_back(ev);
+        }
+        return ctx->events[used++];
+    }
+    static int chunk_for(int n) { return std::max(NMIN, n / 16); }
+
+    void start() {
+        chunk = chunk_for(n);
+        cudaEvent_t fork = event();
+        if (err != cudaSuccess) return;
+        check(cudaEventRecord(fork, ctx->stream));
+        check(cudaStreamWaitEvent(ctx->s_in, fork, 0));
+        check(cudaStreamWaitEvent(ctx->s_out, fork, 0));
+        const size_t col = (size_t)m * sizeof(float);
+        for (int c0 = 0, c1 = std::min(chunk, n); c0 < n && err == cudaSuccess;
+             c0 = c1, c1 = std::min(2 * c1, n)) {
+            check(cudaMemcpy2DAsync(dA + (size_t)c0 * m, col, hA + (size_t)c0 * hlda,
+                                    (size_t)hlda * sizeof(float), col, c1 - c0,
+                                    cudaMemcpyHostToDevice, ctx->s_in));
+            cudaEvent_t ev = event();
+            if (err != cudaSuccess) return;
+            check(cudaEventRecord(ev, ctx->s_in));
+            in_end.push_back(c1);
+            in_ev.push_back(ev);
+        }
+    }
+    // the main stream may read columns [0, c1) after this
+    void need(int c1) {
+        for (size_t k = 0; k < in_end.size(); ++k)
+            if (in_end[k] >= c1) {
+                check(cudaStreamWaitEvent(ctx->stream, in_ev[k], 0));
+                return;
+            }
+    }
+    void after_main() {
+        cudaEvent_t ev = event();
+        if (err != cudaSuccess) return;
+        check(cudaEventRecord(ev, ctx->stream));
+        check(cudaStreamWaitEvent(ctx->s_out, ev, 0));
+    }
+    void send_r(int r0, int nr, int c0, int nc) {
+        check(cudaMemcpy2DAsync(hR + r0 + (size_t)c0 * hldr, (size_t)hldr * sizeof(float),
+                                dR + r0 + (size_t)c0 * n, (size_t)n * sizeof(float),
+                                (size_t)nr * sizeof(float), nc, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    // R12 of node (c0, 2h) has just been produced
+    void r12_final(int c0, int h) {
+        after_main();
+        send_r(c0, h, c0 + h, h);
+    }
+    // the subtree on columns [c0, c0 + w) is done: its Q columns and diagonal block of R are final
+    void cols_final(int c0, int w) {
+        after_main();
+        const size_t col = (size_t)m * sizeof(float);
+        check(cudaMemcpy2DAsync(hA + (size_t)c0 * hlda, (size_t)hlda * sizeof(float),
+                                dA + (size_t)c0 * m, col, col, w, cudaMemcpyDeviceToHost, ctx->s_out));
+        send_r(c0, w, c0, w);
+    }
+    void finish() {
+        need(n);   // joins s_in (already waited for by the top node unless something failed)
+        cudaEvent_t ev = event();
+        if (err != cudaSuccess) return;
+        check(cudaEventRecord(ev, ctx->s_out));
+        check(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    }
+};
+
 struct Recursion {
     later_b200_ctx* ctx;
     later_b200_ctx::Plan* p;
     CUtensorMap q128, q256, q64;
+    HostPipe* pipe = nullptr;
     cudaError_t err = cudaSuccess;
     long launches = 0;
 
@@ -118,14 +214,16 @@ struct Recursion {
         if (err != cudaSuccess) return;
         cudaStream_t st = ctx->stream;
         if (w <= NMIN) {
+            if (pipe && c0 == 0) pipe->need(NMIN);
             check(panel_qr128(st, ctx->num_sms, p->m, p->A + (long)c0 * p->lda, p->lda,
                               p->R + c0 + (long)c0 * p->ldr, p->ldr, p->Qh + (long)c0 * p->ldh,
                               p->ldh, p->panel_scratch));
             launches += 4;
-            return;
+        } else {
+            qr(c0, w / 2);
+            node_tail(c0, w);
         }
-        qr(c0, w / 2);
-        node_tail(c0, w);
+        if (pipe && w == pipe->chunk) pipe->cols_final(c0, w);
     }
 
     // Everything of node (c0, w) after its left recursion: R12 = Q1^T A2, A2 -= Q1 R12, right half.
@@ -137,11 +235,22 @@ struct Recursion {
         float* R12 = p->R + c0 + (long)(c0 + h) * p->ldr;
         // R12 = Q1^T A2 (fp32 into R, fp16 copy for the update)
         const int splits = choose_gram_splits(ctx->num_sms, h, h, bn, p->m);
+        if (c0 == 0) {
+            // Left spine: A2 is still the caller's input, so its fp16 shadow is made here (everywhere
+            // else the update that last wrote A2 has refreshed it).
+            if (pipe) pipe->need(w);
+            const int vec_ok = (p->lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p->A) & 15) == 0);
+            dim3 grid((unsigned)std::min<long>((p->m / 8 + 255) / 256, 64), (unsigned)(w - h));
+            check(launch_pdl(cast_shadow_kernel, grid, dim3(256), 0, st, (const float*)p->A,
+                             (long)p->lda, p->m, h, w, p->Qh, p->ldh, vec_ok));
+            launches += 1;
+        }
         // (the mirror block R21, which the algorithm never produces, is written as zero on the way)
         check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, c0 + h, h,
                       R12, p->ldr, p->R12h, h, p->part, splits,
                       p->R + (c0 + h) + (long)c0 * p->ldr));
         launches += splits > 1 ? 2 : 1;
+        if (pipe && w > pipe->chunk) pipe->r12_final(c0, h);
         // A2 -= Q1 R12, refreshing A2's fp16 shadow
         CUtensorMap r12map;
         HalfMatrix rm{p->R12h, h, h, h};
@@ -163,8 +272,10 @@ struct Recursion {
 int validate(later_b200_ctx* ctx, int m, int n, const void* A, int lda, const void* R, int ldr) {
     if (!ctx) return LATER_B200_EINVAL;
     if (!A || !R) return fail(ctx, LATER_B200_EINVAL, "null matrix pointer");
-    if (n <= 0 || n % NMIN != 0)
-        return fail(ctx, LATER_B200_EINVAL, "n must be a positive multiple of 128");
+    // the halving recursion reaches the 128-column base case only from n = 128 * 2^k (the reference's
+    // panel rejects anything else, QR/panel.cu:12-15)
+    if (n < NMIN || n % NMIN != 0 || ((n / NMIN) & (n / NMIN - 1)) != 0)
+        return fail(ctx, LATER_B200_EINVAL, "n must be 128 * 2^k");
     if (m < n) return fail(ctx, LATER_B200_EINVAL, "m must be >= n");
     if (m % 8 != 0) return fail(ctx, LATER_B200_EINVAL, "m must be a multiple of 8");
     if (lda < m || ldr < n) return fail(ctx, LATER_B200_EINVAL, "leading dimension too small");
@@ -183,6 +294,7 @@ int prepare_plan(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R,
     ctx->arena.reset();
     auto& p = ctx->plan;
     p.m = m; p.n = n; p.A = A; p.lda = lda; p.R = R; p.ldr = ldr;
+    p.hA = nullptr; p.hlda = 0; p.hR = nullptr; p.hldr = 0;
     p.ldh = w.ldh;
     p.Qh = static_cast<__half*>(ctx->arena.alloc(w.qh_bytes));
     p.R12h = w.r12h_bytes ? static_cast<__half*>(ctx->arena.alloc(w.r12h_bytes)) : nullptr;
@@ -196,11 +308,10 @@ int prepare_plan(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R,
     return 0;
 }
 
-// Enqueues the whole factorisation on ctx->stream (directly, or into an ongoing capture).
-// Stages of one factorisation.  ALL is the whole thing; LEFT + REST are the same launches split at
-// the top node (left recursion | top-level gram + update + right recursion) so that the host entry
-// point can overlap them with the PCIe transfers of the other half.
-enum Stage : int { STAGE_ALL = 0, STAGE_LEFT = 1, STAGE_REST = 2 };
+// Enqueues one factorisation on ctx->stream (directly, or into an ongoing capture): the plain
+// launch sequence for a device matrix, or the same with the PCIe copies of the host entry point
+// forked around it.
+enum Stage : int { STAGE_ALL = 0, STAGE_HOST = 1 };
 
 int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
     auto& p = ctx->plan;
@@ -213,20 +324,19 @@ int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
         (e = make_tensor_map_f16(&rec.q256, qm, 64, 256)) != cudaSuccess ||
         (e = make_tensor_map_f16(&rec.q64, qm, 64, 64)) != cudaSuccess)
         return cuda_fail(ctx, e, "tensor map encode");
-    // fp16 shadow of the not-yet-factored input columns this stage will read as A2 operands
-    const int cast_lo = stage == STAGE_REST ? p.n / 2 : NMIN;
-    const int cast_hi = stage == STAGE_LEFT ? p.n / 2 : p.n;
-    if (cast_hi > cast_lo) {
-        const int vec_ok = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-        dim3 grid((unsigned)std::min<long>((p.m / 8 + 255) / 256, 64), (unsigned)(cast_hi - cast_lo));
-        if ((e = launch_pdl(cast_shadow_kernel, grid, dim3(256), 0, ctx->stream, (const float*)p.A,
-                            (long)p.lda, p.m, cast_lo, cast_hi, p.Qh, p.ldh, vec_ok)) != cudaSuccess)
-            return cuda_fail(ctx, e, "cast launch");
-        rec.launches += 1;
+    HostPipe pipe;
+    if (stage == STAGE_HOST) {
+        pipe.ctx = ctx;
+        pipe.hA = p.hA; pipe.hlda = p.hlda; pipe.hR = p.hR; pipe.hldr = p.hldr;
+        pipe.m = p.m; pipe.n = p.n; pipe.dA = p.A; pipe.dR = p.R;
+        pipe.start();
+        rec.pipe = &pipe;
     }
-    if (stage == STAGE_ALL) rec.qr(0, p.n);
-    else if (stage == STAGE_LEFT) rec.qr(0, p.n / 2);
-    else rec.node_tail(0, p.n);
+    rec.qr(0, p.n);
+    if (stage == STAGE_HOST) {
+        pipe.finish();   // always rejoin the side streams, also after an error (capture must close)
+        if (pipe.err != cudaSuccess) return cuda_fail(ctx, pipe.err, "host pipeline");
+    }
     if (rec.err != cudaSuccess) return cuda_fail(ctx, rec.err, "rgsqrf enqueue");
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "rgsqrf launch");
@@ -236,7 +346,8 @@ int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
 
 bool same_plan(const later_b200_ctx::Plan& a, const later_b200_ctx::Plan& b) {
     return a.valid && b.valid && a.m == b.m && a.n == b.n && a.A == b.A && a.lda == b.lda &&
-           a.R == b.R && a.ldr == b.ldr && a.Qh == b.Qh && a.arena_gen == b.arena_gen;
+           a.R == b.R && a.ldr == b.ldr && a.Qh == b.Qh && a.arena_gen == b.arena_gen &&
+           a.hA == b.hA && a.hlda == b.hlda && a.hR == b.hR && a.hldr == b.hldr;
 }
 
 // Runs one stage on ctx->stream: replays the cached graph of that stage when shapes and pointers
@@ -246,7 +357,7 @@ int run_stage(later_b200_ctx* ctx, int stage) {
     if (!ctx->use_graph) {
         long l = 0;
         int rc = enqueue_stage(ctx, stage, &l);
-        ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + l;
+        ctx->launches = l;
         return rc;
     }
     auto& slot = ctx->graphs[stage];
@@ -256,7 +367,7 @@ int run_stage(later_b200_ctx* ctx, int stage) {
     if (!slot.exec && !(slot.seen && same_plan(slot.plan, ctx->plan))) {
         long l = 0;
         int rc = enqueue_stage(ctx, stage, &l);
-        ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + l;
+        ctx->launches = l;
         slot.plan = ctx->plan;
         slot.seen = true;
         return rc;
@@ -264,7 +375,7 @@ int run_stage(later_b200_ctx* ctx, int stage) {
     if (slot.exec && same_plan(slot.plan, ctx->plan)) {
         e = cudaGraphLaunch(slot.exec, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
-        ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + slot.launches;
+        ctx->launches = slot.launches;
         return 0;
     }
     if (slot.exec) {
@@ -273,7 +384,7 @@ int run_stage(later_b200_ctx* ctx, int stage) {
         if (!same_plan(slot.plan, ctx->plan)) {   // a different problem: start over with a direct launch
             long l = 0;
             int rc = enqueue_stage(ctx, stage, &l);
-            ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + l;
+            ctx->launches = l;
             slot.plan = ctx->plan;
             slot.seen = true;
             return rc;
@@ -304,7 +415,7 @@ int run_stage(later_b200_ctx* ctx, int stage) {
     if (e != cudaSuccess) { slot.exec = nullptr; return cuda_fail(ctx, e, "graph instantiate"); }
     slot.plan = ctx->plan;
     slot.launches = launches;
-    ctx->launches = (stage == STAGE_REST ? ctx->launches : 0) + launches;
+    ctx->launches = launches;
     e = cudaGraphLaunch(slot.exec, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
     return 0;
@@ -385,7 +496,7 @@ int later_b200_destroy(later_b200_ctx* ctx) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
-    for (auto& ev : ctx->ev)
+    for (auto& ev : ctx->events)
         if (ev) cudaEventDestroy(ev);
     if (ctx->dA) cudaFree(ctx->dA);
     if (ctx->dR) cudaFree(ctx->dR);
@@ -439,67 +550,28 @@ int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda
         if ((e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)) != cudaSuccess)
             return cuda_fail(ctx, e, "copy streams");
-        for (auto& ev : ctx->ev)
-            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess)
-                return cuda_fail(ctx, e, "events");
     }
-    float* dA = ctx->dA;
-    float* dR = ctx->dR;
-    const size_t colA = (size_t)m * sizeof(float), colR = (size_t)n * sizeof(float);
-    auto h2d = [&](int c0, int nc) {
-        return cudaMemcpy2DAsync(dA + (size_t)c0 * m, colA, hA + (size_t)c0 * lda,
-                                 (size_t)lda * sizeof(float), colA, nc, cudaMemcpyHostToDevice, ctx->s_in);
-    };
-    auto d2h_q = [&](int c0, int nc) {
-        return cudaMemcpy2DAsync(hA + (size_t)c0 * lda, (size_t)lda * sizeof(float), dA + (size_t)c0 * m,
-                                 colA, colA, nc, cudaMemcpyDeviceToHost, ctx->s_out);
-    };
-    auto d2h_r = [&](int r0, int nr, int c0, int nc) {
-        return cudaMemcpy2DAsync(hR + r0 + (size_t)c0 * ldr, (size_t)ldr * sizeof(float),
-                                 dR + r0 + (size_t)c0 * n, colR, (size_t)nr * sizeof(float), nc,
-                                 cudaMemcpyDeviceToHost, ctx->s_out);
-    };
-    // order the copies after whatever the caller already enqueued on the context's stream
-    if ((e = cudaEventRecord(ctx->ev[4], ctx->stream)) != cudaSuccess ||
-        (e = cudaStreamWaitEvent(ctx->s_in, ctx->ev[4], 0)) != cudaSuccess ||
-        (e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[4], 0)) != cudaSuccess)
-        return cuda_fail(ctx, e, "stream ordering");
-    if ((rc = rgsqrf_prepare(ctx, m, n, dA, m, dR, n)) != 0) return rc;
-
-    if (n < 2 * NMIN) {
-        // single panel: nothing to overlap
-        if ((e = h2d(0, n)) != cudaSuccess || (e = cudaEventRecord(ctx->ev[0], ctx->s_in)) != cudaSuccess ||
-            (e = cudaStreamWaitEvent(ctx->stream, ctx->ev[0], 0)) != cudaSuccess)
-            return cuda_fail(ctx, e, "H2D A");
-        if ((rc = run_stage(ctx, STAGE_ALL)) != 0) return rc;
-        if ((e = cudaEventRecord(ctx->ev[2], ctx->stream)) != cudaSuccess ||
-            (e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[2], 0)) != cudaSuccess ||
-            (e = d2h_q(0, n)) != cudaSuccess || (e = d2h_r(0, n, 0, n)) != cudaSuccess)
-            return cuda_fail(ctx, e, "D2H Q/R");
-    } else {
-        // Pipelined: the left half of A is factored while the right half is still crossing PCIe;
-        // the left half of Q and R11 go back while the right half is being factored.
-        const int h = n / 2;
-        if ((e = h2d(0, h)) != cudaSuccess || (e = cudaEventRecord(ctx->ev[0], ctx->s_in)) != cudaSuccess ||
-            (e = h2d(h, n - h)) != cudaSuccess || (e = cudaEventRecord(ctx->ev[1], ctx->s_in)) != cudaSuccess)
-            return cuda_fail(ctx, e, "H2D A");
-        if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev[0], 0)) != cudaSuccess)
-            return cuda_fail(ctx, e, "wait H2D left");
-        if ((rc = run_stage(ctx, STAGE_LEFT)) != 0) return rc;
-        if ((e = cudaEventRecord(ctx->ev[2], ctx->stream)) != cudaSuccess ||
-            (e = cudaStreamWaitEvent(ctx->stream, ctx->ev[1], 0)) != cudaSuccess)
-            return cuda_fail(ctx, e, "wait H2D right");
-        if ((rc = run_stage(ctx, STAGE_REST)) != 0) return rc;
-        if ((e = cudaEventRecord(ctx->ev[3], ctx->stream)) != cudaSuccess)
-            return cuda_fail(ctx, e, "record");
-        if ((e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[2], 0)) != cudaSuccess ||
-            (e = d2h_q(0, h)) != cudaSuccess || (e = d2h_r(0, h, 0, h)) != cudaSuccess ||
-            (e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[3], 0)) != cudaSuccess ||
-            (e = d2h_q(h, n - h)) != cudaSuccess || (e = d2h_r(0, n, h, n - h)) != cudaSuccess ||
-            (e = d2h_r(h, n - h, 0, h)) != cudaSuccess)
-            return cuda_fail(ctx, e, "D2H Q/R");
+    if ((rc = rgsqrf_prepare(ctx, m, n, ctx->dA, m, ctx->dR, n)) != 0) return rc;
+    auto& p = ctx->plan;
+    p.hA = hA; p.hlda = lda; p.hR = hR; p.hldr = ldr;
+    // The copies only overlap (and can only be graph nodes that replay safely) from page-locked
+    // memory; with pageable buffers the same sequence is enqueued directly and the runtime stages it.
+    cudaPointerAttributes pa{}, pr{};
+    const bool pinned = cudaPointerGetAttributes(&pa, hA) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&pr, hR) == cudaSuccess && pr.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    const bool graph = ctx->use_graph;
+    if (!pinned) ctx->use_graph = false;
+    rc = run_stage(ctx, STAGE_HOST);
+    ctx->use_graph = graph;
+    if (rc) {
+        cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->s_out);
+        cudaStreamSynchronize(ctx->stream);
+        (void)cudaGetLastError();
+        return rc;
     }
-    if ((e = cudaStreamSynchronize(ctx->s_out)) != cudaSuccess) return cuda_fail(ctx, e, "D2H sync");
+    // the side streams were joined back into the context's stream
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return cuda_fail(ctx, e, "sync");
     return 0;
 }

@@ -111,7 +111,9 @@ def later_rgsqrf(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int
 
 def later_rgsqrf_host(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int,
                       R: torch.Tensor, ldr: int) -> None:
-    """Same with HOST (ideally pinned) buffers; H2D and D2H copies happen inside the call."""
+    """Same with HOST (ideally pinned) buffers; H2D and D2H copies happen inside the call, overlapped
+    with the factorisation.  R's blocks below the block diagonal (granularity max(128, n/16)) are
+    not written (include/later_b200.h)."""
     ctxt = ctxt or default_context()
     if A.is_cuda or R.is_cuda:
         raise ValueError("later_rgsqrf_host takes host tensors")

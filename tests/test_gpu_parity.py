@@ -227,15 +227,41 @@ def test_deterministic_and_graph_equals_stream(qr):
 
 
 # ------------------------------------------------------------------------------ boundary behaviour
-def test_host_entry_point_matches_device_entry_point(qr, ctx):
+def _host_block_mask(n):
+    """Entries of hR the host entry point writes: the block upper triangle at its transfer
+    granularity max(128, n/16) (include/later_b200.h)."""
+    c = max(128, n // 16)
+    blk = np.arange(n) // c
+    return blk[:, None] <= blk[None, :]
+
+
+@pytest.mark.parametrize("m,n,pinned,pad", [(1024, 256, True, 0), (1024, 128, True, 0),
+                                            (4096, 2048, True, 0), (8192, 4096, True, 0),
+                                            (2048, 512, False, 0), (2048, 512, True, 24)])
+def test_host_entry_point_matches_device_entry_point(qr, ctx, m, n, pinned, pad):
+    """Same bits as the device entry point, on the first (direct), second (graph capture) and third
+    (graph replay) call; entries below the block diagonal of hR are left alone."""
     rng = np.random.default_rng(10)
-    A0 = rng.standard_normal((1024, 256), dtype=np.float32)
+    A0 = rng.standard_normal((m, n), dtype=np.float32)
     Qd, Rd = run_rgsqrf(qr, ctx, A0)
-    hA = torch.empty((256, 1024), dtype=torch.float32).pin_memory().t()
-    hA.copy_(torch.from_numpy(A0))
-    hR = torch.empty((256, 256), dtype=torch.float32).pin_memory().t()
-    qr.later_rgsqrf_host(ctx, 1024, 256, hA, 1024, hR, 256)
-    assert np.array_equal(hA.numpy(), Qd) and np.array_equal(hR.numpy(), Rd)
+    lda, ldr = m + pad, n + pad
+    bufA = torch.empty((n, lda), dtype=torch.float32)
+    bufR = torch.empty((n, ldr), dtype=torch.float32)
+    if pinned:
+        bufA, bufR = bufA.pin_memory(), bufR.pin_memory()
+    hA, hR = bufA.t()[:m], bufR.t()[:n]
+    mask = _host_block_mask(n)
+    for _ in range(3):
+        bufA.fill_(-3.0)
+        hA.copy_(torch.from_numpy(A0))
+        bufR.fill_(7.0)
+        qr.later_rgsqrf_host(ctx, m, n, hA, lda, hR, ldr)
+        assert np.array_equal(hA.numpy(), Qd)
+        got = hR.numpy()
+        assert np.array_equal(got[mask], Rd[mask])
+        assert np.all(got[~mask] == 7.0)
+        if pad:
+            assert np.all(bufA.t()[m:].numpy() == -3.0) and np.all(bufR.t()[n:].numpy() == 7.0)
 
 
 def test_leading_dimensions_are_honoured(qr, ctx):
@@ -254,6 +280,11 @@ def test_argument_errors_do_not_launch(qr, ctx):
     R = qr.colmajor_empty(192, 192)
     with pytest.raises(qr.LaterError) as e:
         qr.later_rgsqrf(ctx, 512, 192, A, 512, R, 192)          # n not a multiple of 128
+    assert e.value.code == -1
+    A = qr.colmajor_empty(512, 384)
+    R = qr.colmajor_empty(384, 384)
+    with pytest.raises(qr.LaterError) as e:
+        qr.later_rgsqrf(ctx, 512, 384, A, 512, R, 384)          # n = 3 * 128: halving never reaches 128
     assert e.value.code == -1
     A = qr.colmajor_empty(128, 256)
     R = qr.colmajor_empty(256, 256)
