@@ -103,12 +103,14 @@ Workspace plan_workspace(int num_sms, int m, int n) {
     return w;
 }
 
-// The PCIe legs of later_b200_rgsqrf_host, woven into the recursion.  Column c of A is first read
-// by the node whose right half contains it, and only the left spine of the tree ever reads
-// columns nothing has updated yet - so the matrix is sent in doubling pieces [0,c) [c,2c) [2c,4c) ...
-// and each left-spine node waits for just the piece it is about to touch.  On the way out, an R12
-// block is final as soon as its Gram product is, and a block of Q columns (with the diagonal block
-// of R) as soon as its subtree is done; each goes back while the factorisation continues.
+// The PCIe legs of later_b200_rgsqrf_host.  The host path runs the factorisation LEFT-LOOKING over
+// column pieces of width max(128, n/16): piece j is touched only once it has arrived, receives the
+// Gram/update of every node of the recursion tree whose right half contains it (widest first - the
+// order the recursion applies them in), is then factored by the ordinary recursion, and is final.
+// Same operations on the same operands as the recursive order, so the result is bit-identical to
+// the device entry point; but everything left of the piece is final when the piece starts and the
+// piece is final when it ends, so A streams in, and Q and R stream out, at PCIe speed with the
+// factorisation hidden underneath.
 // The copies run on two side streams forked from and joined back into the main stream, so the
 // same enqueue code works directly and inside a stream capture (where they become memcpy nodes).
 struct HostPipe {
@@ -145,15 +147,14 @@ struct HostPipe {
         check(cudaStreamWaitEvent(ctx->s_in, fork, 0));
         check(cudaStreamWaitEvent(ctx->s_out, fork, 0));
         const size_t col = (size_t)m * sizeof(float);
-        for (int c0 = 0, c1 = std::min(chunk, n); c0 < n && err == cudaSuccess;
-             c0 = c1, c1 = std::min(2 * c1, n)) {
+        for (int c0 = 0; c0 < n && err == cudaSuccess; c0 += chunk) {
             check(cudaMemcpy2DAsync(dA + (size_t)c0 * m, col, hA + (size_t)c0 * hlda,
-                                    (size_t)hlda * sizeof(float), col, c1 - c0,
-                                    cudaMemcpyHostToDevice, ctx->s_in));
+                                    (size_t)hlda * sizeof(float), col, chunk, cudaMemcpyHostToDevice,
+                                    ctx->s_in));
             cudaEvent_t ev = event();
             if (err != cudaSuccess) return;
             check(cudaEventRecord(ev, ctx->s_in));
-            in_end.push_back(c1);
+            in_end.push_back(c0 + chunk);
             in_ev.push_back(ev);
         }
     }
@@ -165,32 +166,21 @@ struct HostPipe {
                 return;
             }
     }
-    void after_main() {
+    // piece [c0, c0 + w) is final: its Q columns and rows [0, c0 + w) of its R columns go back
+    void cols_final(int c0, int w) {
         cudaEvent_t ev = event();
         if (err != cudaSuccess) return;
         check(cudaEventRecord(ev, ctx->stream));
         check(cudaStreamWaitEvent(ctx->s_out, ev, 0));
-    }
-    void send_r(int r0, int nr, int c0, int nc) {
-        check(cudaMemcpy2DAsync(hR + r0 + (size_t)c0 * hldr, (size_t)hldr * sizeof(float),
-                                dR + r0 + (size_t)c0 * n, (size_t)n * sizeof(float),
-                                (size_t)nr * sizeof(float), nc, cudaMemcpyDeviceToHost, ctx->s_out));
-    }
-    // R12 of node (c0, 2h) has just been produced
-    void r12_final(int c0, int h) {
-        after_main();
-        send_r(c0, h, c0 + h, h);
-    }
-    // the subtree on columns [c0, c0 + w) is done: its Q columns and diagonal block of R are final
-    void cols_final(int c0, int w) {
-        after_main();
         const size_t col = (size_t)m * sizeof(float);
         check(cudaMemcpy2DAsync(hA + (size_t)c0 * hlda, (size_t)hlda * sizeof(float),
                                 dA + (size_t)c0 * m, col, col, w, cudaMemcpyDeviceToHost, ctx->s_out));
-        send_r(c0, w, c0, w);
+        check(cudaMemcpy2DAsync(hR + (size_t)c0 * hldr, (size_t)hldr * sizeof(float),
+                                dR + (size_t)c0 * n, (size_t)n * sizeof(float),
+                                (size_t)(c0 + w) * sizeof(float), w, cudaMemcpyDeviceToHost, ctx->s_out));
     }
     void finish() {
-        need(n);   // joins s_in (already waited for by the top node unless something failed)
+        need(n);   // joins s_in (already waited for by the last piece unless something failed)
         cudaEvent_t ev = event();
         if (err != cudaSuccess) return;
         check(cudaEventRecord(ev, ctx->s_out));
@@ -202,7 +192,6 @@ struct Recursion {
     later_b200_ctx* ctx;
     later_b200_ctx::Plan* p;
     CUtensorMap q128, q256, q64;
-    HostPipe* pipe = nullptr;
     cudaError_t err = cudaSuccess;
     long launches = 0;
 
@@ -214,7 +203,6 @@ struct Recursion {
         if (err != cudaSuccess) return;
         cudaStream_t st = ctx->stream;
         if (w <= NMIN) {
-            if (pipe && c0 == 0) pipe->need(NMIN);
             check(panel_qr128(st, ctx->num_sms, p->m, p->A + (long)c0 * p->lda, p->lda,
                               p->R + c0 + (long)c0 * p->ldr, p->ldr, p->Qh + (long)c0 * p->ldh,
                               p->ldh, p->panel_scratch));
@@ -223,48 +211,70 @@ struct Recursion {
             qr(c0, w / 2);
             node_tail(c0, w);
         }
-        if (pipe && w == pipe->chunk) pipe->cols_final(c0, w);
+    }
+
+    void cast(int c0, int c1) {
+        const int vec_ok = (p->lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p->A) & 15) == 0);
+        dim3 grid((unsigned)std::min<long>((p->m / 8 + 255) / 256, 64), (unsigned)(c1 - c0));
+        check(launch_pdl(cast_shadow_kernel, grid, dim3(256), 0, ctx->stream, (const float*)p->A,
+                         (long)p->lda, p->m, c0, c1, p->Qh, p->ldh, vec_ok));
+        launches += 1;
+    }
+
+    // R12 = Q1^T A2 and A2 -= Q1 R12 for Q1 = columns [c0, c0 + h), A2 = columns [cb, cb + nb).
+    // The recursion calls it with A2 = the whole right half of node (c0, 2h); the left-looking
+    // host schedule with one piece of it.  The split-K factor is always the one of the whole node,
+    // so that both orders add the same partial sums in the same order.
+    void gram_update(int c0, int h, int cb, int nb, bool zero_mirror) {
+        if (err != cudaSuccess) return;
+        cudaStream_t st = ctx->stream;
+        const int bn = nb % 256 == 0 ? gram_bn(h) : 128;
+        const int splits = choose_gram_splits(ctx->num_sms, h, h, gram_bn(h), p->m);
+        // (the mirror block R21, which the algorithm never produces, is written as zero on the way)
+        check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, cb, nb,
+                      p->R + c0 + (long)cb * p->ldr, p->ldr, p->R12h, h, p->part, splits,
+                      zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr));
+        launches += splits > 1 ? 2 : 1;
+        CUtensorMap r12map;
+        HalfMatrix rm{p->R12h, h, nb, h};
+        const int ubn = nb % 256 == 0 ? update_bn(h) : 128;
+        check(make_tensor_map_f16(&r12map, rm, 64, ubn));
+        if (update_uses_tma(h) && p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
+            check(tc_update_tma(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, nb, p->A, p->m,
+                                p->n, p->lda, cb, p->Qh, p->ldh, true));
+        } else {   // (TMA also needs 16-byte aligned column strides)
+            check(tc_update(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, nb,
+                            p->A + (long)cb * p->lda, p->lda, p->Qh + (long)cb * p->ldh, p->ldh, true));
+        }
+        launches += 1;
+    }
+
+    // The host entry point's schedule (see HostPipe).
+    void left_looking(HostPipe* pipe) {
+        const int P = pipe->chunk, pieces = p->n / P;
+        for (int j = 0; j < pieces && err == cudaSuccess; ++j) {
+            const int cj = j * P;
+            pipe->need(cj + P);
+            // piece 0 is cast by the left spine of its own recursion; later pieces are read by a Gram
+            // product before anything has updated them
+            if (j > 0) cast(cj, cj + P);
+            for (int s = pieces; s >= 2; s /= 2) {
+                const int a = j / s * s;            // node (a, s) in pieces; j in its right half?
+                if (j - a >= s / 2) gram_update(a * P, s / 2 * P, cj, P, false);
+            }
+            qr(cj, P);
+            pipe->cols_final(cj, P);
+        }
     }
 
     // Everything of node (c0, w) after its left recursion: R12 = Q1^T A2, A2 -= Q1 R12, right half.
     void node_tail(int c0, int w) {
         if (err != cudaSuccess) return;
-        cudaStream_t st = ctx->stream;
         const int h = w / 2;
-        const int bn = gram_bn(h);
-        float* R12 = p->R + c0 + (long)(c0 + h) * p->ldr;
-        // R12 = Q1^T A2 (fp32 into R, fp16 copy for the update)
-        const int splits = choose_gram_splits(ctx->num_sms, h, h, bn, p->m);
-        if (c0 == 0) {
-            // Left spine: A2 is still the caller's input, so its fp16 shadow is made here (everywhere
-            // else the update that last wrote A2 has refreshed it).
-            if (pipe) pipe->need(w);
-            const int vec_ok = (p->lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p->A) & 15) == 0);
-            dim3 grid((unsigned)std::min<long>((p->m / 8 + 255) / 256, 64), (unsigned)(w - h));
-            check(launch_pdl(cast_shadow_kernel, grid, dim3(256), 0, st, (const float*)p->A,
-                             (long)p->lda, p->m, h, w, p->Qh, p->ldh, vec_ok));
-            launches += 1;
-        }
-        // (the mirror block R21, which the algorithm never produces, is written as zero on the way)
-        check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, c0 + h, h,
-                      R12, p->ldr, p->R12h, h, p->part, splits,
-                      p->R + (c0 + h) + (long)c0 * p->ldr));
-        launches += splits > 1 ? 2 : 1;
-        if (pipe && w > pipe->chunk) pipe->r12_final(c0, h);
-        // A2 -= Q1 R12, refreshing A2's fp16 shadow
-        CUtensorMap r12map;
-        HalfMatrix rm{p->R12h, h, h, h};
-        const int ubn = update_bn(h);
-        check(make_tensor_map_f16(&r12map, rm, 64, ubn));
-        if (update_uses_tma(h) && p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
-            check(tc_update_tma(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, h, p->A, p->m,
-                                p->n, p->lda, c0 + h, p->Qh, p->ldh, true));
-        } else {   // (TMA also needs 16-byte aligned column strides)
-            check(tc_update(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, h,
-                            p->A + (long)(c0 + h) * p->lda, p->lda, p->Qh + (long)(c0 + h) * p->ldh,
-                            p->ldh, true));
-        }
-        launches += 1;
+        // Left spine: A2 is still the caller's input, so its fp16 shadow is made here (everywhere
+        // else the update that last wrote A2 has refreshed it).
+        if (c0 == 0) cast(h, w);
+        gram_update(c0, h, c0 + h, h, true);
         qr(c0 + h, h);
     }
 };
@@ -330,9 +340,10 @@ int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
         pipe.hA = p.hA; pipe.hlda = p.hlda; pipe.hR = p.hR; pipe.hldr = p.hldr;
         pipe.m = p.m; pipe.n = p.n; pipe.dA = p.A; pipe.dR = p.R;
         pipe.start();
-        rec.pipe = &pipe;
+        rec.left_looking(&pipe);
+    } else {
+        rec.qr(0, p.n);
     }
-    rec.qr(0, p.n);
     if (stage == STAGE_HOST) {
         pipe.finish();   // always rejoin the side streams, also after an error (capture must close)
         if (pipe.err != cudaSuccess) return cuda_fail(ctx, pipe.err, "host pipeline");
