@@ -13,6 +13,7 @@
 #include "../../include/later_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "context.h"
 #include "tc_gemm.cuh"
@@ -21,6 +22,7 @@ namespace lb {
 namespace {
 
 inline long round_up(long x, long a) { return (x + a - 1) / a * a; }
+constexpr int BK = 64;   // k-block of the tcgen05 kernels (tc_gemm.cu)
 
 __global__ void maxabs_kernel(const float* __restrict__ X, long ld, int rows, int cols,
                               unsigned* __restrict__ slot) {
@@ -90,6 +92,7 @@ struct Planes {
 };
 
 struct Ormqr {
+    int kChunk = 2048;
     later_b200_ctx* ctx;
     cudaStream_t st;
     cudaError_t err = cudaSuccess;
@@ -122,10 +125,27 @@ struct Ormqr {
         check(make_tensor_map_f16(&bl, Blo, 64, bn));
         if (err != cudaSuccess) return;
         p.dscale = unscale;
-        check(tc_gemm_launch(st, ctx->num_sms, a_mn_major, bn, first_epi, ah, bh, p));
+        // The tensor core adds into its fp32 accumulator with truncation, so the error of one long
+        // accumulation grows linearly with the number of MMA steps (measured at K = 32768: 1.1e-5
+        // of max|Q| in one piece, 4.8e-6 / 2.3e-6 / 1.2e-6 in chunks of 8192 / 4096 / 2048, against
+        // 1.0e-6 for the reference's fp32 FMA chain).  The hi*hi term is therefore cut into chunks
+        // of kChunk along K; each chunk accumulates in TMEM and is added to C in fp32
+        // round-to-nearest by the epilogue.  The two cross terms are 2^-11 smaller, and so is their
+        // truncation error: they run over the whole K.
+        const int kb_all = p.kb_total;
+        const int kb_chunk = kChunk / BK;
+        for (int kb0 = 0; kb0 < kb_all; kb0 += kb_chunk) {
+            TcGemmParams q = p;
+            q.kb_total = q.kb_per_split = std::min(kb_chunk, kb_all - kb0);
+            if (a_mn_major) q.a_c1 += kb0 * BK; else q.a_c0 += kb0 * BK;
+            q.b_c0 += kb0 * BK;
+            check(tc_gemm_launch(st, ctx->num_sms, a_mn_major, bn, kb0 == 0 ? first_epi : next_epi, ah,
+                                 bh, q));
+            launches += 1;
+        }
         check(tc_gemm_launch(st, ctx->num_sms, a_mn_major, bn, next_epi, ah, bl, p));
         check(tc_gemm_launch(st, ctx->num_sms, a_mn_major, bn, next_epi, al, bh, p));
-        launches += 3;
+        launches += 2;
     }
 };
 
@@ -167,6 +187,7 @@ int ormqr_impl(later_b200_ctx* ctx, int m, int n, float* W, int ldw, const float
 
     Ormqr o{};
     o.ctx = ctx; o.st = ctx->stream;
+    if (const char* v = getenv("LB_ORMQR_KCHUNK")) o.kChunk = std::max(BK, atoi(v) / BK * BK);
     o.slot = reinterpret_cast<unsigned*>(scal + 32);
     o.sW = scal; o.sY = scal + 2; o.sK = scal + 4; o.unscale = scal + 6;
     o.check(cudaMemsetAsync(scal, 0, 64 * sizeof(float), o.st));

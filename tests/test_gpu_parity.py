@@ -173,6 +173,7 @@ def _factor_device(qr, ctx, A0: torch.Tensor):
     (16384, 16384, "uniform", 5.1e-4, 7.9e-4),   # config 2; reference on its own input: 2.52e-4 / 3.90e-4
     (262144, 256, "normal", 1e-4, 1e-5),         # config 3
     (131072, 1024, "normal", 2e-4, 2e-5),        # one 8-GPU shard of config 4
+    (32768, 32768, "normal", 4.2e-4, 2.8e-4),    # config 5; reference on the same input: 2.07e-4 / 1.35e-4
 ])
 def test_full_size_properties(qr, ctx, m, n, dist, back_max, orth_max):
     g = torch.Generator(device="cuda").manual_seed(3000)
@@ -330,6 +331,31 @@ def test_ormqr_large_is_fp32_faithful(qr, ctx):
     err = (W.double() - ref).abs().max().item() / ref.abs().max().item()
     err32 = ((torch.eye(m, n, device="cuda") - W0 @ Y0[:n, :n].t()).double() - ref).abs().max().item() / ref.abs().max().item()
     assert err <= max(4 * err32, 2e-6)
+
+
+def test_ormqr_long_accumulation_is_fp32_faithful(qr, ctx):
+    """K = 8192: the tensor core's truncating fp32 accumulate would cost a digit here (and more at
+    config 5's K = 32768) unless the hi*hi term is accumulated in chunks; the full later_ormqr
+    (merge step + I - W Y^T) must stay at the level of an fp32 FMA implementation."""
+    m = n = 8192
+    h = n // 2
+    g = torch.Generator(device="cuda").manual_seed(14)
+    Y0 = torch.tril(torch.randn(m, n, device="cuda", generator=g) * 0.02, -1)
+    Y0.diagonal().fill_(1.0)
+    W0 = torch.randn(m, n, device="cuda", generator=g) * 0.02
+    W, Y = qr.to_colmajor(W0), qr.to_colmajor(Y0)
+    qr.later_ormqr(m, n, W, m, Y, m, ctxt=ctx)
+
+    def form(Wm, Ym):
+        Wm = Wm.clone()
+        Wm[:, h:] -= Wm[:, :h] @ (Ym[:, :h].t() @ Wm[:, h:])
+        return torch.eye(m, n, device="cuda", dtype=Wm.dtype) - Wm @ Ym[:n, :n].t()
+
+    ref = form(W0.double(), Y0.double())
+    scale = ref.abs().max().item()
+    err = (W.double() - ref).abs().max().item() / scale
+    err32 = (form(W0, Y0).double() - ref).abs().max().item() / scale     # fp32 cuBLAS, TF32 off
+    assert err <= max(2 * err32, 1e-6)
 
 
 # ------------------------------------------------------------------------------ TSQR back-multiply
