@@ -60,6 +60,15 @@ int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, floa
 int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda, float* hR,
                            int ldr);
 
+/* Host in, device out: the columns of hA (host, ideally page-locked) are copied into A (device) and
+ * factored as they arrive, exactly as in later_b200_rgsqrf_host, but Q (in A) and R stay on the
+ * device and the call is asynchronous on the context's stream like later_b200_rgsqrf.  This is the
+ * local step of the row-sharded multi-GPU factorisation, whose Q still needs the TSQR
+ * back-multiplication before it can leave the device.  hA must stay valid until the stream has
+ * passed the call. */
+int later_b200_rgsqrf_stream_in(later_b200_ctx* ctx, int m, int n, const float* hA, int hlda, float* A,
+                                int lda, float* R, int ldr);
+
 /* 128-column tall-skinny panel only (reference mgs_caqr_panel_256x128, QR/panel.cu:10-63).
  * n must be 128.  Qh (optional, device fp16, leading dimension ldqh) receives the fp16 copy. */
 int later_b200_panel_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr);

@@ -21,6 +21,8 @@ SYMBOLS = {
     "later_b200_workspace_bytes": (C.c_size_t, [_c_ctx, C.c_int, C.c_int]),
     "later_b200_rgsqrf": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "later_b200_rgsqrf_host": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "later_b200_rgsqrf_stream_in": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                              C.c_void_p, C.c_int]),
     "later_b200_panel_qr": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "later_b200_tsqr_apply": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "later_b200_ormqr": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

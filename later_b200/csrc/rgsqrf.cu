@@ -118,8 +118,9 @@ struct HostPipe {
     float* hA = nullptr; long hlda = 0;
     float* hR = nullptr; long hldr = 0;
     int m = 0, n = 0, chunk = NMIN;
-    float* dA = nullptr;       // device staging, column-major with leading dimensions m and n
-    float* dR = nullptr;
+    float* dA = nullptr; long ldda = 0;   // device matrices the factorisation works on
+    float* dR = nullptr; long lddr = 0;
+    bool copy_out = true;      // false: Q and R stay on the device (later_b200_rgsqrf_stream_in)
     std::vector<int> in_end;   // right edge of each H2D piece
     std::vector<cudaEvent_t> in_ev;
     size_t used = 0;
@@ -148,9 +149,9 @@ struct HostPipe {
         check(cudaStreamWaitEvent(ctx->s_out, fork, 0));
         const size_t col = (size_t)m * sizeof(float);
         for (int c0 = 0; c0 < n && err == cudaSuccess; c0 += chunk) {
-            check(cudaMemcpy2DAsync(dA + (size_t)c0 * m, col, hA + (size_t)c0 * hlda,
-                                    (size_t)hlda * sizeof(float), col, chunk, cudaMemcpyHostToDevice,
-                                    ctx->s_in));
+            check(cudaMemcpy2DAsync(dA + (size_t)c0 * ldda, (size_t)ldda * sizeof(float),
+                                    hA + (size_t)c0 * hlda, (size_t)hlda * sizeof(float), col, chunk,
+                                    cudaMemcpyHostToDevice, ctx->s_in));
             cudaEvent_t ev = event();
             if (err != cudaSuccess) return;
             check(cudaEventRecord(ev, ctx->s_in));
@@ -168,15 +169,17 @@ struct HostPipe {
     }
     // piece [c0, c0 + w) is final: its Q columns and rows [0, c0 + w) of its R columns go back
     void cols_final(int c0, int w) {
+        if (!copy_out) return;
         cudaEvent_t ev = event();
         if (err != cudaSuccess) return;
         check(cudaEventRecord(ev, ctx->stream));
         check(cudaStreamWaitEvent(ctx->s_out, ev, 0));
         const size_t col = (size_t)m * sizeof(float);
         check(cudaMemcpy2DAsync(hA + (size_t)c0 * hlda, (size_t)hlda * sizeof(float),
-                                dA + (size_t)c0 * m, col, col, w, cudaMemcpyDeviceToHost, ctx->s_out));
+                                dA + (size_t)c0 * ldda, (size_t)ldda * sizeof(float), col, w,
+                                cudaMemcpyDeviceToHost, ctx->s_out));
         check(cudaMemcpy2DAsync(hR + (size_t)c0 * hldr, (size_t)hldr * sizeof(float),
-                                dR + (size_t)c0 * n, (size_t)n * sizeof(float),
+                                dR + (size_t)c0 * lddr, (size_t)lddr * sizeof(float),
                                 (size_t)(c0 + w) * sizeof(float), w, cudaMemcpyDeviceToHost, ctx->s_out));
     }
     void finish() {
@@ -263,6 +266,11 @@ struct Recursion {
                 if (j - a >= s / 2) gram_update(a * P, s / 2 * P, cj, P, false);
             }
             qr(cj, P);
+            // R stays on the device: its blocks below this piece's diagonal block, which no Gram
+            // epilogue of this schedule covers, are cleared here (the host copy-out skips them)
+            if (!pipe->copy_out && cj + P < p->n)
+                check(cudaMemset2DAsync(p->R + (cj + P) + (long)cj * p->ldr, (size_t)p->ldr * sizeof(float),
+                                        0, (size_t)(p->n - cj - P) * sizeof(float), P, ctx->stream));
             pipe->cols_final(cj, P);
         }
     }
@@ -338,7 +346,9 @@ int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
     if (stage == STAGE_HOST) {
         pipe.ctx = ctx;
         pipe.hA = p.hA; pipe.hlda = p.hlda; pipe.hR = p.hR; pipe.hldr = p.hldr;
-        pipe.m = p.m; pipe.n = p.n; pipe.dA = p.A; pipe.dR = p.R;
+        pipe.m = p.m; pipe.n = p.n;
+        pipe.dA = p.A; pipe.ldda = p.lda; pipe.dR = p.R; pipe.lddr = p.ldr;
+        pipe.copy_out = p.hR != nullptr;
         pipe.start();
         rec.left_looking(&pipe);
     } else {
@@ -538,6 +548,40 @@ int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, floa
     return rgsqrf_device(ctx, m, n, A, lda, R, ldr);
 }
 
+// Shared by the two host-input entry points: factor the device matrix (dA, dR) while its columns
+// arrive from hA; with hR != nullptr, Q (into hA) and R (into hR) also stream back.
+static int rgsqrf_streamed(later_b200_ctx* ctx, int m, int n, float* hA, int hlda, float* hR, int hldr,
+                           float* dA, int ldda, float* dR, int lddr) {
+    cudaError_t e;
+    if (!ctx->s_in) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(ctx, e, "copy streams");
+    }
+    int rc = rgsqrf_prepare(ctx, m, n, dA, ldda, dR, lddr);
+    if (rc) return rc;
+    auto& p = ctx->plan;
+    p.hA = hA; p.hlda = hlda; p.hR = hR; p.hldr = hldr;
+    // The copies only overlap (and can only be graph nodes that replay safely) from page-locked
+    // memory; with pageable buffers the same sequence is enqueued directly and the runtime stages it.
+    cudaPointerAttributes pa{}, pr{};
+    const bool pinned = cudaPointerGetAttributes(&pa, hA) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                        (!hR || (cudaPointerGetAttributes(&pr, hR) == cudaSuccess &&
+                                 pr.type == cudaMemoryTypeHost));
+    (void)cudaGetLastError();
+    const bool graph = ctx->use_graph;
+    if (!pinned) ctx->use_graph = false;
+    rc = run_stage(ctx, STAGE_HOST);
+    ctx->use_graph = graph;
+    if (rc) {
+        cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->s_out);
+        cudaStreamSynchronize(ctx->stream);
+        (void)cudaGetLastError();
+    }
+    return rc;   // the side streams have been joined back into the context's stream
+}
+
 int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda, float* hR,
                            int ldr) {
     int rc = validate(ctx, m, n, hA, lda, hR, ldr);
@@ -557,34 +601,19 @@ int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda
         if ((e = cudaMalloc(&ctx->dR, r_bytes)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc R");
         ctx->dR_bytes = r_bytes;
     }
-    if (!ctx->s_in) {
-        if ((e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
-            (e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)) != cudaSuccess)
-            return cuda_fail(ctx, e, "copy streams");
-    }
-    if ((rc = rgsqrf_prepare(ctx, m, n, ctx->dA, m, ctx->dR, n)) != 0) return rc;
-    auto& p = ctx->plan;
-    p.hA = hA; p.hlda = lda; p.hR = hR; p.hldr = ldr;
-    // The copies only overlap (and can only be graph nodes that replay safely) from page-locked
-    // memory; with pageable buffers the same sequence is enqueued directly and the runtime stages it.
-    cudaPointerAttributes pa{}, pr{};
-    const bool pinned = cudaPointerGetAttributes(&pa, hA) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
-                        cudaPointerGetAttributes(&pr, hR) == cudaSuccess && pr.type == cudaMemoryTypeHost;
-    (void)cudaGetLastError();
-    const bool graph = ctx->use_graph;
-    if (!pinned) ctx->use_graph = false;
-    rc = run_stage(ctx, STAGE_HOST);
-    ctx->use_graph = graph;
-    if (rc) {
-        cudaStreamSynchronize(ctx->s_in);
-        cudaStreamSynchronize(ctx->s_out);
-        cudaStreamSynchronize(ctx->stream);
-        (void)cudaGetLastError();
-        return rc;
-    }
-    // the side streams were joined back into the context's stream
+    if ((rc = rgsqrf_streamed(ctx, m, n, hA, lda, hR, ldr, ctx->dA, m, ctx->dR, n)) != 0) return rc;
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return cuda_fail(ctx, e, "sync");
     return 0;
+}
+
+int later_b200_rgsqrf_stream_in(later_b200_ctx* ctx, int m, int n, const float* hA, int hlda, float* A,
+                                int lda, float* R, int ldr) {
+    int rc = validate(ctx, m, n, A, lda, R, ldr);
+    if (rc) return rc;
+    if (!hA || hlda < m) return fail(ctx, LATER_B200_EINVAL, "bad host matrix");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    return rgsqrf_streamed(ctx, m, n, const_cast<float*>(hA), hlda, nullptr, 0, A, lda, R, ldr);
 }
 
 int later_b200_panel_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {

@@ -124,6 +124,23 @@ def later_rgsqrf_host(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda
         ctxt._raise(rc)
 
 
+def later_rgsqrf_stream_in(ctxt: Context | None, m: int, n: int, hA: torch.Tensor, hlda: int,
+                           A: torch.Tensor, lda: int, R: torch.Tensor, ldr: int) -> None:
+    """Host in, device out: hA (host, ideally pinned) is copied into A (device) column piece by
+    column piece and factored as it arrives; Q (in A) and R stay on the device.  Asynchronous on the
+    context's stream; hA must stay alive until the stream has passed the call."""
+    ctxt = ctxt or default_context()
+    if hA.is_cuda or not A.is_cuda or not R.is_cuda:
+        raise ValueError("later_rgsqrf_stream_in takes a host hA and device A, R")
+    _check_colmajor("hA", hA, m, n, hlda)
+    _check_colmajor("A", A, m, n, lda)
+    _check_colmajor("R", R, n, n, ldr)
+    rc = lib.later_b200_rgsqrf_stream_in(ctxt._h, m, n, hA.data_ptr(), hlda, A.data_ptr(), lda,
+                                         R.data_ptr(), ldr)
+    if rc != 0:
+        ctxt._raise(rc)
+
+
 def mgs_caqr_panel_256x128(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int,
                            R: torch.Tensor, ldr: int, work=None) -> None:
     """QR of an m x 128 panel (reference QR/panel.cu:10-63)."""

@@ -33,12 +33,16 @@ def tsqr_rgsqrf(m_local: int, n: int, A: torch.Tensor, lda: int, R: torch.Tensor
                 local_qr: Callable | None = None,
                 stack_qr: Callable | None = None,
                 apply_w: Callable | None = None,
-                ctxs=None) -> None:
+                ctxs=None, host_A: torch.Tensor | None = None) -> None:
     """In place: A (this rank's m_local x n row block, column-major) <- its block of the global Q;
-    R (n x n) <- the global R factor (identical on every rank)."""
+    R (n x n) <- the global R factor (identical on every rank).  With `host_A` (host tensor of the
+    same shape, ideally pinned) the row block is taken from there instead: it crosses PCIe while the
+    local factorisation is already working on the columns that have arrived, and A is output only."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
 
+    if local_qr is not None and host_A is not None:
+        raise ValueError("host_A needs the built-in local_qr")
     if local_qr is None:
         from . import qr as _qr
         if ctxs is None:
@@ -46,7 +50,10 @@ def tsqr_rgsqrf(m_local: int, n: int, A: torch.Tensor, lda: int, R: torch.Tensor
         main_ctx, stack_ctx = ctxs
 
         def local_qr(m, n_, a, lda_, r, ldr_):
-            _qr.later_rgsqrf(main_ctx, m, n_, a, lda_, r, ldr_)
+            if host_A is not None:
+                _qr.later_rgsqrf_stream_in(main_ctx, m, n_, host_A, host_A.stride(1), a, lda_, r, ldr_)
+            else:
+                _qr.later_rgsqrf(main_ctx, m, n_, a, lda_, r, ldr_)
 
         def stack_qr(m, n_, s, lds, r, ldr_):
             _qr.later_rgsqrf(stack_ctx, m, n_, s, lds, r, ldr_)

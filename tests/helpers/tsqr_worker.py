@@ -25,7 +25,8 @@ def main():
     A0 = A_glob[rank * mloc:(rank + 1) * mloc].clone()
     A = qr.to_colmajor(A0)
     R = qr.colmajor_empty(n, n)
-    tsqr_rgsqrf(mloc, n, A, mloc, R, n)
+    ctxs = (qr.Context(), qr.Context())
+    tsqr_rgsqrf(mloc, n, A, mloc, R, n, ctxs=ctxs)
     torch.cuda.synchronize()
     # every rank must hold the same R, bit for bit
     Rs = [torch.empty_like(R.contiguous()) for _ in range(world)]
@@ -41,6 +42,16 @@ def main():
     orth = float(torch.linalg.norm(G) / n)
     ok = same and back < 5e-4 and orth < 5e-5 and bool((R.diagonal() > 0).all()) \
         and float(torch.tril(R, -1).abs().max()) == 0.0
+    # same factorisation with the row block arriving from pinned host memory during the local QR
+    hA = torch.empty((n, mloc), dtype=torch.float32).pin_memory()
+    hA.copy_(A0.t())
+    A2 = qr.colmajor_empty(mloc, n)
+    R2 = qr.colmajor_empty(n, n)
+    for _ in range(3):      # direct launch, graph capture, graph replay
+        A2.fill_(float("nan"))
+        tsqr_rgsqrf(mloc, n, A2, mloc, R2, n, ctxs=ctxs, host_A=hA.t())
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(A2, A) and torch.equal(R2, R)
     if rank == 0:
         # against the single-GPU factorisation of the whole matrix
         c = qr.Context()

@@ -18,7 +18,7 @@ def _declared_symbols():
 def test_header_declares_the_expected_entry_points():
     names = _declared_symbols()
     for must in ("later_b200_create", "later_b200_destroy", "later_b200_rgsqrf",
-                 "later_b200_rgsqrf_host", "later_b200_ormqr", "later_b200_ormqr2",
+                 "later_b200_rgsqrf_host", "later_b200_rgsqrf_stream_in", "later_b200_ormqr", "later_b200_ormqr2",
                  "later_b200_panel_qr", "later_b200_tsqr_apply", "later_b200_workspace_bytes"):
         assert must in names
 

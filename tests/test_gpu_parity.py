@@ -265,6 +265,27 @@ def test_host_entry_point_matches_device_entry_point(qr, ctx, m, n, pinned, pad)
             assert np.all(bufA.t()[m:].numpy() == -3.0) and np.all(bufR.t()[n:].numpy() == 7.0)
 
 
+def test_stream_in_matches_device_entry_point(qr, ctx):
+    """Host in, device out (the local step of the multi-GPU path): same bits as factoring a matrix
+    that is already on the device, on the direct, the capturing and the replaying call."""
+    m, n = 8192, 1024
+    rng = np.random.default_rng(15)
+    A0 = rng.standard_normal((m, n), dtype=np.float32)
+    Qd, Rd = run_rgsqrf(qr, ctx, A0)
+    hA = torch.empty((n, m), dtype=torch.float32).pin_memory().t()
+    hA.copy_(torch.from_numpy(A0))
+    A = qr.colmajor_empty(m, n)
+    R = qr.colmajor_empty(n, n)
+    for _ in range(3):
+        A.fill_(float("nan"))
+        R.fill_(float("nan"))
+        qr.later_rgsqrf_stream_in(ctx, m, n, hA, m, A, m, R, n)
+        torch.cuda.synchronize()
+        assert np.array_equal(hA.numpy(), A0)                       # the host copy is input only
+        assert np.array_equal(A.cpu().numpy(), Qd)
+        assert np.array_equal(R.cpu().numpy(), Rd)                  # including the zeros below
+
+
 def test_leading_dimensions_are_honoured(qr, ctx):
     rng = np.random.default_rng(11)
     A0 = rng.standard_normal((512, 256), dtype=np.float32)
