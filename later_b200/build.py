@@ -25,6 +25,7 @@ SOURCES = {
     "tc_gemm.cu": [],
     "tc_update.cu": [],
     "panel.cu": [],
+    "panel_tc.cu": [],
     "rgsqrf.cu": [],
     "ormqr.cu": [],
     "compat.cu": ["-rdc=true"],

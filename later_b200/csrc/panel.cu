@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 namespace lb {
 namespace {
@@ -610,7 +611,7 @@ int gram_grid(int m, int num_sms) {
 }
 
 struct ScratchLayout {
-    size_t part_off, g_off, fac_off, info_off, total;
+    size_t part_off, g_off, fac_off, info_off, tc_off, total;
 };
 ScratchLayout scratch_layout(int m, int num_sms) {
     ScratchLayout L{};
@@ -621,6 +622,7 @@ ScratchLayout scratch_layout(int m, int num_sms) {
     L.fac_off = off;  off += sizeof(PanelFactors);
     off = (off + 255) & ~(size_t)255;
     L.info_off = off; off += 256;
+    L.tc_off = off;   off += sizeof(TcApplyFactors);
     L.total = off;
     return L;
 }
@@ -631,12 +633,25 @@ ScratchLayout scratch_layout(int m, int num_sms) {
 size_t panel_scratch_bytes(int m, int num_sms) { return scratch_layout(m, num_sms).total; }
 
 cudaError_t panel_init() {
-    return cudaFuncSetAttribute(apply128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(ApplySmem));
+    cudaError_t e = cudaFuncSetAttribute(apply128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(ApplySmem));
+    return e != cudaSuccess ? e : tc_apply_init();
+}
+
+// LB_APPLY_TC = 0 / 1 forces the forward-substitution / tensor-core apply (tests, profiling).
+static int apply_tc_override() {
+    const char* s = getenv("LB_APPLY_TC");
+    return s ? atoi(s) : -1;
+}
+
+bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc) {
+    const int ov = apply_tc_override();
+    const bool tc_ok = lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+    return tc_ok && (ov == 1 || (ov != 0 && allow_tc && m >= kTcApplyMinRows));
 }
 
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
-                        long ldr, __half* Qh, long ldqh, void* scratch) {
+                        long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc) {
     const ScratchLayout L = scratch_layout(m, num_sms);
     uint8_t* base = static_cast<uint8_t*>(scratch);
     double* part = reinterpret_cast<double*>(base + L.part_off);
@@ -652,6 +667,9 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
                          (const double*)part, ggrid, G, fac->flag)) != cudaSuccess) return le;
     if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr, fac,
                          info)) != cudaSuccess) return le;
+    if (panel_uses_tc_apply(m, A, lda, allow_tc))
+        return panel_apply_tc(stream, num_sms, m, A, lda, R, ldr, Qh, ldqh,
+                              reinterpret_cast<TcApplyFactors*>(base + L.tc_off));
     // programmatic dependent launch: the apply grid may start while the Cholesky grid is running
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((m + APPLY_ROWS - 1) / APPLY_ROWS);

@@ -23,9 +23,35 @@ size_t panel_scratch_bytes(int m, int num_sms);
 
 // A[m x 128] (fp32, ld lda) -> Q in place; R[128 x 128] (fp32, ld ldr) upper triangular with the
 // strictly lower part zeroed; Qh (optional) receives the fp16 copy of Q (ld ldqh).
+// allow_tc: tall panels (m >= kTcApplyMinRows) may form Q with the split-precision tensor-core
+// apply (panel_tc.cu), whose Q is accurate to ~1e-6 instead of ~1e-7: the recursion, which consumes
+// Q rounded to fp16 anyway, says yes; the stand-alone panel entry point, which replaces the
+// reference's all-fp32 panel, says no.
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
-                        long ldr, __half* Qh, long ldqh, void* scratch);
+                        long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc);
 
 cudaError_t panel_init();
+// Which apply panel_qr128 will use (4 launches per panel with forward substitution, 5 with the
+// tensor-core apply: + the triangular inverse).
+bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc);
+
+// ---- tensor-core apply for tall panels (panel_tc.cu)
+// Rows from which panel_qr128 switches from the fp32 forward-substitution apply (hidden behind the
+// Cholesky kernel on short panels) to the split-precision tcgen05 apply (HBM-bound).
+constexpr int kTcApplyMinRows = 65536;
+
+struct TcApplyFactors {
+    // three fp16 planes t1 + t2 + t3 = diag(1/s) R^-1 * 2^e (to 2^-33), column-major
+    __half T[3][kPanelWidth * kPanelWidth];
+    float colscale[kPanelWidth];             // s_k: power of two with ||a_k|| s_k in [2^13, 2^14)
+    float unscale;                           // 2^-e
+    float pad[127];
+};
+
+cudaError_t tc_apply_init();
+// Q = A R^-1 for an m x 128 panel whose R (fp32, upper triangular) is already in place; needs
+// lda % 4 == 0 and a 16-byte aligned A.
+cudaError_t panel_apply_tc(cudaStream_t stream, int num_sms, int m, float* A, long lda, const float* R,
+                           long ldr, __half* Qh, long ldqh, TcApplyFactors* fac);
 
 }  // namespace lb

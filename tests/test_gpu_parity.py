@@ -159,6 +159,34 @@ def test_panel_vs_reference_golden(qr, ctx, name):
     assert np.abs(Q[::8, :] - g["Q_rows8"]).max() <= 2e-5
 
 
+@pytest.mark.parametrize("m,dist", [(1000, "normal"), (16384, "uniform"), (131072, "normal"),
+                                    (262144, "uniform")])
+def test_tensor_core_apply_vs_forward_substitution(qr, ctx, m, dist, monkeypatch):
+    """Tall panels inside the recursion form Q = A R^-1 with the split-precision tcgen05 apply
+    (panel_tc.cu).  Same R, and a Q that agrees with the fp32 forward-substitution apply far below
+    the fp16 rounding that the recursion applies to Q next (4.9e-4)."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    A0 = (torch.rand if dist == "uniform" else torch.randn)(m, 128, device="cuda", generator=g)
+    out = {}
+    for tc in ("0", "1"):
+        monkeypatch.setenv("LB_APPLY_TC", tc)
+        A = qr.to_colmajor(A0)
+        R = qr.colmajor_empty(128, 128)
+        R.fill_(float("nan"))
+        qr.mgs_caqr_panel_256x128(ctx, m, 128, A, m, R, 128)
+        torch.cuda.synchronize()
+        assert ctx.last_launch_count == (5 if tc == "1" else 4)
+        out[tc] = (A, R)
+    (Q0, R0), (Q1, R1) = out["0"], out["1"]
+    assert torch.equal(R0, R1)
+    assert (Q1 - Q0).abs().max().item() <= 4e-6 * Q0.abs().max().item()
+    eye = torch.eye(128, device="cuda", dtype=torch.float64)
+    orth = torch.linalg.matrix_norm(Q1.double().t() @ Q1.double() - eye).item()
+    back = (torch.linalg.matrix_norm(Q1.double() @ torch.triu(R1).double() - A0.double())
+            / torch.linalg.matrix_norm(A0.double())).item()
+    assert orth <= 2e-5 and back <= 1e-6
+
+
 # ------------------------------------------------------------------------------ full-size properties
 def _factor_device(qr, ctx, A0: torch.Tensor):
     m, n = A0.shape
