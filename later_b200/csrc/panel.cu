@@ -611,7 +611,7 @@ int gram_grid(int m, int num_sms) {
 }
 
 struct ScratchLayout {
-    size_t part_off, g_off, fac_off, info_off, tc_off, total;
+    size_t part_off, g_off, fac_off, info_off, tc_off, colmax_off, total;
 };
 ScratchLayout scratch_layout(int m, int num_sms) {
     ScratchLayout L{};
@@ -623,6 +623,7 @@ ScratchLayout scratch_layout(int m, int num_sms) {
     off = (off + 255) & ~(size_t)255;
     L.info_off = off; off += 256;
     L.tc_off = off;   off += sizeof(TcApplyFactors);
+    L.colmax_off = off; off += (size_t)PW * kColmaxParts * sizeof(float);
     L.total = off;
     return L;
 }
@@ -644,10 +645,23 @@ static int apply_tc_override() {
     return s ? atoi(s) : -1;
 }
 
+// LB_GRAM_I8 = 0 keeps the fp64 (DMMA) Gram kernel everywhere.
+bool panel_uses_i8_gram(int m, int num_sms, const float* A, long lda, bool allow_tc) {
+    const char* s = getenv("LB_GRAM_I8");
+    if (s && atoi(s) == 0) return false;
+    const bool aligned = lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+    return allow_tc && aligned && m >= kTcApplyMinRows && panel_gram_i8_fits(m, num_sms);
+}
+
 bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc) {
     const int ov = apply_tc_override();
     const bool tc_ok = lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
     return tc_ok && (ov == 1 || (ov != 0 && allow_tc && m >= kTcApplyMinRows));
+}
+
+int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_tc) {
+    return 4 + (panel_uses_tc_apply(m, A, lda, allow_tc) ? 1 : 0) +
+           (panel_uses_i8_gram(m, num_sms, A, lda, allow_tc) ? 1 : 0);
 }
 
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
@@ -658,11 +672,18 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
     double* G = reinterpret_cast<double*>(base + L.g_off);
     PanelFactors* fac = reinterpret_cast<PanelFactors*>(base + L.fac_off);
     int* info = reinterpret_cast<int*>(base + L.info_off);
-    const int ggrid = gram_grid(m, num_sms);
+    int ggrid = gram_grid(m, num_sms);
 
     cudaError_t le;
-    if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream,
-                         (const float*)A, lda, m, part)) != cudaSuccess) return le;
+    if (panel_uses_i8_gram(m, num_sms, A, lda, allow_tc)) {
+        ggrid = panel_gram_i8_grid(m, num_sms);
+        if ((le = panel_gram_i8(stream, num_sms, m, A, lda, reinterpret_cast<float*>(base + L.colmax_off), part,
+                                info + 1)) != cudaSuccess)
+            return le;
+    } else if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream,
+                                (const float*)A, lda, m, part)) != cudaSuccess) {
+        return le;
+    }
     if ((le = launch_pdl(gram128_reduce_kernel, dim3((GRAM_ELEMS + 31) / 32), dim3(1024), 0, stream,
                          (const double*)part, ggrid, G, fac->flag)) != cudaSuccess) return le;
     if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr, fac,

@@ -34,6 +34,8 @@ cudaError_t panel_init();
 // Which apply panel_qr128 will use (4 launches per panel with forward substitution, 5 with the
 // tensor-core apply: + the triangular inverse).
 bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc);
+bool panel_uses_i8_gram(int m, int num_sms, const float* A, long lda, bool allow_tc);
+int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_tc);
 
 // ---- tensor-core apply for tall panels (panel_tc.cu)
 // Rows from which panel_qr128 switches from the fp32 forward-substitution apply (hidden behind the
@@ -49,6 +51,14 @@ struct TcApplyFactors {
 };
 
 cudaError_t tc_apply_init();
+// Integer-tensor-core Gram matrix of an m x 128 panel into per-CTA partials laid out like the DMMA
+// kernel's ([cta][upper 32 x 32 block][r][c] doubles); *_grid = number of partials it writes.
+int panel_gram_i8_grid(int m, int num_sms);
+bool panel_gram_i8_fits(int m, int num_sms);
+// colmax_part: kColmaxParts floats of scratch per column (written by the kernel's own first pass).
+constexpr int kColmaxParts = 64;
+cudaError_t panel_gram_i8(cudaStream_t stream, int num_sms, int m, const float* A, long lda,
+                          float* colmax_part, double* part, int* info);
 // Q = A R^-1 for an m x 128 panel whose R (fp32, upper triangular) is already in place; needs
 // lda % 4 == 0 and a 16-byte aligned A.
 cudaError_t panel_apply_tc(cudaStream_t stream, int num_sms, int m, float* A, long lda, const float* R,

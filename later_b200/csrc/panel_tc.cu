@@ -18,6 +18,21 @@
 //                       A buffers and accumulators are double-buffered: converting tile t+1 overlaps
 //                       the MMAs of tile t and the drain of tile t-1.
 //
+//   gram128_i8_kernel   the panel's Gram matrix G = A^T A on the INTEGER tensor path, exact in the
+//                       sense of the Ozaki scheme: every column is brought to 31-bit fixed point with
+//                       a power-of-two scale derived from its largest entry (colmax128_kernel, a
+//                       read-only first pass that leaves the panel in L2 when it fits), each
+//                       integer is cut into four balanced base-256 digits (one XOR-ADD pair: the
+//                       digits are the bytes of (x + 0x00808080) ^ 0x00808080), and the digit planes
+//                       D_s are multiplied with tcgen05.mma kind::i8 into four int32 TMEM accumulators,
+//                       one per weight 256^(s+t), s + t = 3 .. 6 (10 of the 16 plane pairs; the six
+//                       dropped pairs are below 2^-26 of a product).  Integer accumulation is exact,
+//                       so the result does not depend on summation order; the accumulators are read
+//                       ONCE per CTA, recombined and unscaled in fp64, and handed to the same
+//                       fixed-order reduce + fp64 Cholesky as the DMMA Gram kernel of panel.cu.  That
+//                       kernel is bounded by the fp64 pipe (64 FMA/clk/SM: 0.87 ms for 2^20 rows);
+//                       this one by HBM / the int8 tensor rate.
+//
 // The fp32 forward-substitution kernel (panel.cu) stays in use for short panels, where it hides
 // behind the Cholesky kernel; this path adds the inverse (~15 us) to the dependency chain and only
 // pays off when the apply itself is the long pole (m >= kTcApplyMinRows).
@@ -365,12 +380,255 @@ apply128_tc_kernel(const __grid_constant__ CUtensorMap mapT1, const __grid_const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05.mma kind::i8: signed 8-bit operands, int32 accumulate, K = 32 per instruction.
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// instruction descriptor: D = S32 (2 at [4,6)), A and B signed 8 bit (1 at [7,10) and [10,13)),
+// both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((PW >> 3) << 17) | ((PW >> 4) << 24);
+
+constexpr int GI8_WORKERS = 256;
+constexpr int GI8_THREADS = GI8_WORKERS + 32;
+constexpr int DIGIT_PLANE_BYTES = PW * 128;                  // 128 columns x 128 rows of int8
+constexpr int DIGIT_BUF_BYTES = 4 * DIGIT_PLANE_BYTES;       // four digit planes of one 128-row tile
+constexpr int GI8_SMEM = 2 * DIGIT_BUF_BYTES + PW * 4 + PW * 8 + 128 + 1024;
+constexpr int GI8_MAX_TILES_PER_CTA = 256;                   // 2^15 rows x (4 pairs x 2^14) < 2^31
+constexpr int NTRI_BLOCKS = 10, GBLK = 32, G_ELEMS = NTRI_BLOCKS * GBLK * GBLK;
+
+__host__ __device__ inline int tri_index4(int bi, int bj) { return bi * 4 - bi * (bi - 1) / 2 + (bj - bi); }
+
+// max_i |a_ic| of every column, as kColmaxParts per-block partial maxima (no atomics, no zeroing).
+__global__ void __launch_bounds__(256)
+colmax128_kernel(const float* __restrict__ A, long lda, int m, float* __restrict__ colmax_part) {
+    __shared__ float red[8];
+    const int c = blockIdx.y;
+    pdl_trigger();
+    pdl_wait();
+    const float* src = A + (long)c * lda;
+    float mx = 0.f;
+    for (int i = (blockIdx.x * 256 + threadIdx.x) * 4; i < m; i += kColmaxParts * 256 * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);      // m % 8 == 0, aligned
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+        colmax_part[c * kColmaxParts + blockIdx.x] = mx;
+    }
+}
+
+__global__ void __launch_bounds__(GI8_THREADS, 1)
+gram128_i8_kernel(const float* __restrict__ A, long lda, int m, const float* __restrict__ colmax_part,
+                  double* __restrict__ part, int* __restrict__ info) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    float* scale = reinterpret_cast<float*>(smem_gen + 2 * DIGIT_BUF_BYTES);           // 2^E_c
+    double* unscale = reinterpret_cast<double*>(smem_gen + 2 * DIGIT_BUF_BYTES + PW * 4);   // 2^-E_c
+    const uint32_t bar_base = smem_base + 2 * DIGIT_BUF_BYTES + PW * 4 + PW * 8;
+    auto a_full = [&](int b) { return bar_base + 8u * b; };
+    auto a_empty = [&](int b) { return bar_base + 8u * (2 + b); };
+    const uint32_t acc_done = bar_base + 8u * 4;
+    const uint32_t tmem_slot = bar_base + 8u * 5;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles = (m + PW - 1) / PW;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(a_full(b), GI8_WORKERS);
+                mbar_init(a_empty(b), 1);
+            }
+            mbar_init(acc_done, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_trigger();
+    pdl_wait();          // the panel and the column-norm partials come from predecessors
+
+    if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int n = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n) {
+                const int b = n & 1;
+                mbar_wait(a_full(b), (uint32_t)(n >> 1) & 1u);
+                tc_fence_after_sync();
+                const uint32_t buf = smem_base + b * DIGIT_BUF_BYTES;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (s + t < 3) continue;           // weight 256^(s+t): below 2^-26 of a product
+                        const uint64_t a_desc = make_smem_desc_sw128(buf + s * DIGIT_PLANE_BYTES, 16, 1024);
+                        const uint64_t b_desc = make_smem_desc_sw128(buf + t * DIGIT_PLANE_BYTES, 16, 1024);
+                        // the first pair of every group in issue order: (0,3), (1,3), (2,3), (3,3)
+                        const bool group_start = (t == 3);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_i8(tmem_base + (s + t - 3) * PW, a_desc + 2 * k, b_desc + 2 * k, kIdescI8,
+                                    (n == 0 && group_start && k == 0) ? 0u : 1u);
+                    }
+                }
+                umma_commit(a_empty(b));
+            }
+            umma_commit(acc_done);
+        }
+    } else {
+        // ------------------------------------------------------------------ workers
+        if (tid < PW) {
+            float bound = 0.f;                                           // max_i |a_ic|
+            for (int b = 0; b < kColmaxParts; ++b) bound = fmaxf(bound, colmax_part[tid * kColmaxParts + b]);
+            int e = 0;
+            if (bound > 0.f && isfinite(bound)) frexpf(bound, &e);       // bound < 2^e
+            int E = 30 - e;                                              // |a| 2^E < 2^30
+            E = max(-96, min(96, E));
+            scale[tid] = ldexpf(1.f, E);
+            unscale[tid] = ldexp(1.0, -E);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int q = tid & 7;                  // 16-row chunk of the tile
+        const int cb = tid >> 3;                // columns cb + 32 u
+        bool overflow = false;
+        int n = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n) {
+            const int b = n & 1;
+            mbar_wait(a_empty(b), ((uint32_t)(n >> 1) & 1u) ^ 1u);
+            uint8_t* buf = smem_gen + b * DIGIT_BUF_BYTES;
+            const int row0 = tile * PW + q * 16;
+            {   // this thread's four chunks (16 rows x 1 column each), all 16 loads in flight at once
+                float4 v[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float* src = A + row0 + (long)(cb + 32 * u) * lda;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        v[u][w] = row0 + 4 * w < m ? *reinterpret_cast<const float4*>(src + 4 * w)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = cb + 32 * u;
+                    const float s = scale[c];
+                    uint32_t pl[4][4];           // [digit plane][word of 4 consecutive rows]
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const float f[4] = {v[u][w].x * s, v[u][w].y * s, v[u][w].z * s, v[u][w].w * s};
+                        uint32_t z[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            overflow |= fabsf(f[i]) > 1073741824.f;
+                            // balanced base-256 digits = bytes of (x + 0x00808080) ^ 0x00808080
+                            z[i] = ((uint32_t)__float2int_rn(f[i]) + 0x00808080u) ^ 0x00808080u;
+                        }
+                        const uint32_t lo01 = __byte_perm(z[0], z[1], 0x5140), lo23 = __byte_perm(z[2], z[3], 0x5140);
+                        const uint32_t hi01 = __byte_perm(z[0], z[1], 0x7362), hi23 = __byte_perm(z[2], z[3], 0x7362);
+                        pl[0][w] = __byte_perm(lo01, lo23, 0x5410);
+                        pl[1][w] = __byte_perm(lo01, lo23, 0x7632);
+                        pl[2][w] = __byte_perm(hi01, hi23, 0x5410);
+                        pl[3][w] = __byte_perm(hi01, hi23, 0x7632);
+                    }
+                    // K-major SWIZZLE_128B: one 128-byte row (128 consecutive matrix rows) per column
+                    const uint32_t off = (uint32_t)c * 128 + (uint32_t)((q ^ (c & 7)) << 4);
+#pragma unroll
+                    for (int d = 0; d < 4; ++d)
+                        *reinterpret_cast<uint4*>(buf + d * DIGIT_PLANE_BYTES + off) =
+                            make_uint4(pl[d][0], pl[d][1], pl[d][2], pl[d][3]);
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(a_full(b));
+        }
+        if (overflow) atomicOr(info, 2);        // (Inf / NaN in the panel)
+
+        // ---- drain: G(j,k) 2^(E_j + E_k) = sum_g acc_g(j,k) 256^(g+3), upper 32 x 32 blocks only
+        mbar_wait(acc_done, 0);
+        tc_fence_after_sync();
+        const int quad = warp & 3, half = warp >> 2;
+        const int j = quad * 32 + lane;
+        const double uj = unscale[j];
+        double* dst_cta = part + (long)blockIdx.x * G_ELEMS;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+            const int bj = 2 * half + cc;
+            if (bj < quad) continue;                // strictly lower block: never read
+            double sum[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[i] = 0.0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t d[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + g * PW + bj * 32, d);
+                tmem_ld_wait();
+                const double wgt = (double)(1ull << (8 * (g + 3)));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[i] = fma((double)(int)d[i], wgt, sum[i]);
+            }
+            double* dst = dst_cta + tri_index4(quad, bj) * (GBLK * GBLK) + lane * GBLK;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2)
+                *reinterpret_cast<double2*>(dst + i) =
+                    make_double2(sum[i] * uj * unscale[bj * 32 + i], sum[i + 1] * uj * unscale[bj * 32 + i + 1]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace
 
 size_t tc_apply_scratch_bytes() { return sizeof(TcApplyFactors); }
 
+int panel_gram_i8_grid(int m, int num_sms) {
+    const int tiles = (m + PW - 1) / PW;
+    return tiles < num_sms ? tiles : num_sms;
+}
+
+bool panel_gram_i8_fits(int m, int num_sms) {
+    const int tiles = (m + PW - 1) / PW, grid = panel_gram_i8_grid(m, num_sms);
+    return (tiles + grid - 1) / grid <= GI8_MAX_TILES_PER_CTA;
+}
+
+cudaError_t panel_gram_i8(cudaStream_t stream, int num_sms, int m, const float* A, long lda,
+                          float* colmax_part, double* part, int* info) {
+    cudaError_t e = launch_pdl(colmax128_kernel, dim3(kColmaxParts, PW), dim3(256), 0, stream, A, lda, m,
+                               colmax_part);
+    if (e != cudaSuccess) return e;
+    e = launch_pdl(gram128_i8_kernel, dim3(panel_gram_i8_grid(m, num_sms)), dim3(GI8_THREADS),
+                   (size_t)GI8_SMEM, stream, A, lda, m, (const float*)colmax_part, part, info);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 cudaError_t tc_apply_init() {
-    cudaError_t e = cudaFuncSetAttribute(trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gram128_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI8_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TRINV_SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(apply128_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCA_SMEM);

@@ -209,7 +209,7 @@ struct Recursion {
             check(panel_qr128(st, ctx->num_sms, p->m, p->A + (long)c0 * p->lda, p->lda,
                               p->R + c0 + (long)c0 * p->ldr, p->ldr, p->Qh + (long)c0 * p->ldh,
                               p->ldh, p->panel_scratch, true));
-            launches += panel_uses_tc_apply(p->m, p->A + (long)c0 * p->lda, p->lda, true) ? 5 : 4;
+            launches += panel_launch_count(p->m, ctx->num_sms, p->A + (long)c0 * p->lda, p->lda, true);
         } else {
             qr(c0, w / 2);
             node_tail(c0, w);
@@ -631,7 +631,7 @@ int later_b200_panel_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, fl
     ctx->plan.valid = false;
     void* scratch = ctx->arena.alloc(bytes);
     e = panel_qr128(ctx->stream, ctx->num_sms, m, A, lda, R, ldr, nullptr, 0, scratch, false);
-    ctx->launches = panel_uses_tc_apply(m, A, lda, false) ? 5 : 4;
+    ctx->launches = panel_launch_count(m, ctx->num_sms, A, lda, false);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "panel_qr128");
     return 0;
 }

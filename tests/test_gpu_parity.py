@@ -187,6 +187,33 @@ def test_tensor_core_apply_vs_forward_substitution(qr, ctx, m, dist, monkeypatch
     assert orth <= 2e-5 and back <= 1e-6
 
 
+@pytest.mark.parametrize("m,n,dist", [(65536, 256, "normal"), (131072, 512, "uniform"), (70000, 128, "graded")])
+def test_integer_gram_vs_fp64_gram(qr, m, n, dist, monkeypatch):
+    """Tall panels inside the recursion form G = A^T A on the integer tensor path (Ozaki splitting,
+    tcgen05 kind::i8, exact int32 accumulation; panel_tc.cu).  Against the fp64 DMMA kernel the
+    factorisation must agree to fp32 rounding, far inside the fp16-level parity tolerances."""
+    g = torch.Generator(device="cuda").manual_seed(22)
+    A0 = (torch.rand if dist == "uniform" else torch.randn)(m, n, device="cuda", generator=g)
+    if dist == "graded":      # columns spanning four decades, some entries 1e-4 of their column's largest
+        A0 = A0 * torch.logspace(0, -4, n, device="cuda")[None, :] * (1e-4 + torch.rand(m, 1, device="cuda", generator=g))
+    out = {}
+    for i8 in ("0", "1"):
+        monkeypatch.setenv("LB_GRAM_I8", i8)
+        c = qr.Context()
+        A = qr.to_colmajor(A0)
+        R = qr.colmajor_empty(n, n)
+        qr.later_rgsqrf(c, m, n, A, m, R, n)
+        torch.cuda.synchronize()
+        out[i8] = (A, R, c.last_launch_count)
+        c.close()
+    (Q0, R0, l0), (Q1, R1, l1) = out["0"], out["1"]
+    assert l1 == l0 + n // 128                                   # one more launch per panel (column maxima)
+    assert (R1 - R0).abs().max().item() <= 5e-6 * R0.abs().max().item()
+    # (a last-bit change of R12 can flip fp16 roundings of the update's operands: Q moves at that level)
+    assert (Q1 - Q0).abs().max().item() <= 4.9e-4 * Q0.abs().max().item()
+    assert qr.orthogonality(Q1) <= 1.1 * qr.orthogonality(Q0) + 1e-8
+
+
 # ------------------------------------------------------------------------------ full-size properties
 def _factor_device(qr, ctx, A0: torch.Tensor):
     m, n = A0.shape
