@@ -43,7 +43,7 @@ int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_
 constexpr int kTcApplyMinRows = 65536;
 
 struct TcApplyFactors {
-    // three fp16 planes t1 + t2 + t3 = diag(1/s) R^-1 * 2^e (to 2^-33), column-major
+    // three fp16 planes t1 + t2 + t3 = fp32(diag(1/s) R^-1) * 2^e exactly, column-major
     __half T[3][kPanelWidth * kPanelWidth];
     float colscale[kPanelWidth];             // s_k: power of two with ||a_k|| s_k in [2^13, 2^14)
     float unscale;                           // 2^-e

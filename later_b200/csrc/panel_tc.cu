@@ -12,11 +12,11 @@
 //                       MN-major SWIZZLE_128B operand layout (what TMA would have produced); one
 //                       thread issues Ahi T1 + Ahi T2 + Alo T1 + Ahi T3 (32 tcgen05.mma, M128 N128 K16,
 //                       fp32 accumulation in TMEM, K = 128 so the truncating accumulate is
-//                       harmless); the same eight warps drain the previous tile's accumulator with
-//                       tcgen05.ld and store Q (fp32, in place) and its fp16 shadow directly -
-//                       lanes are consecutive rows, so every store instruction writes one full line.
-//                       A buffers and accumulators are double-buffered: converting tile t+1 overlaps
-//                       the MMAs of tile t and the drain of tile t-1.
+//                       harmless); four drain warps read the accumulator with tcgen05.ld and store Q
+//                       (fp32, in place) and its fp16 shadow directly - lanes are consecutive rows,
+//                       so every store instruction writes one full line.  A buffers and
+//                       accumulators are double-buffered: loading tile t+1 overlaps the MMAs of tile t
+//                       and the stores of tile t-1, so reads and writes stream concurrently.
 //
 //   gram128_i8_kernel   the panel's Gram matrix G = A^T A on the INTEGER tensor path, exact in the
 //                       sense of the Ozaki scheme: every column is brought to 31-bit fixed point with
@@ -42,6 +42,7 @@
 #include "tc_gemm.cuh"
 
 #include <cstdint>
+#include <cstdio>
 
 namespace lb {
 
@@ -51,10 +52,15 @@ namespace {
 
 constexpr int PW = kPanelWidth;            // 128
 constexpr int TS_LD = 136;                 // doubles per row of T in shared memory (8 mod 16)
-constexpr int RS_LD = 129;                 // floats per column of R in shared memory
 constexpr int TRINV_THREADS = 512;
-constexpr size_t TRINV_SMEM = (size_t)PW * TS_LD * sizeof(double) + (size_t)PW * RS_LD * sizeof(float) +
-                              3 * PW * sizeof(double) + 64;
+constexpr int R_PACKED = PW * (PW + 1) / 2;                  // upper triangle, column-packed
+constexpr size_t TRINV_SMEM = (size_t)PW * TS_LD * sizeof(double) + (size_t)R_PACKED * sizeof(double) +
+                              3 * PW * sizeof(double) + 16 * 64 * sizeof(double) + 64;
+
+__device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 
 __device__ __forceinline__ double shfl_xor_f64(double v, int mask) {
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -74,91 +80,118 @@ __device__ __forceinline__ float pow2_scale(float x) {
 __global__ void __launch_bounds__(TRINV_THREADS, 1)
 trinv128_kernel(const float* __restrict__ R, long ldr, TcApplyFactors* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    double* Ts = reinterpret_cast<double*>(smem_raw);                    // T[k][j] at k * TS_LD + j
-    float* Rs = reinterpret_cast<float*>(Ts + PW * TS_LD);               // R(i, k) at k * RS_LD + i
-    double* rinv = reinterpret_cast<double*>(Rs + PW * RS_LD);         // (66048 B: still 8-byte aligned)       // 1 / R(i, i)
+    double* Ts = reinterpret_cast<double*>(smem_raw);                    // T(k, j) at k * TS_LD + j
+    double* Rp = Ts + PW * TS_LD;                                        // R(i, k), i <= k, at k (k+1)/2 + i
+    double* rinv = Rp + R_PACKED;                                        // 1 / R(i, i)
     float* sc = reinterpret_cast<float*>(rinv + PW);                     // column scales s_k
     float* red = sc + PW;                                                // block max reduction
+    double* Sscr = reinterpret_cast<double*>(red + 32);                  // 16 warps x 64 doubles
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto Rat = [&](int i, int k) -> double { return Rp[(k * (k + 1) >> 1) + i]; };
     pdl_trigger();
     pdl_wait();          // R comes from the Cholesky kernel
+#ifdef LB_TRINV_TRACE
+    long long tr[8]; int ntr = 0;
+#define TRINV_MARK() do { __syncthreads(); tr[ntr++] = clock64(); } while (0)
+    TRINV_MARK();
+#else
+#define TRINV_MARK() do {} while (0)
+#endif
 
-    for (int idx = tid; idx < PW * PW; idx += TRINV_THREADS) {
-        const int i = idx & (PW - 1), k = idx >> 7;
-        Rs[k * RS_LD + i] = i <= k ? R[i + (long)k * ldr] : 0.f;
+    // (held in fp64 so that the inner loops below carry no conversions: F2F runs at 16 / clk / SM)
+    {   // thread (i, k0): rows i of columns k0, k0 + 4, ...; all 32 loads in flight before the first use
+        const int i = tid & (PW - 1), k0 = tid >> 7;
+        float r[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) r[t] = R[i + (long)(k0 + 4 * t) * ldr];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int k = k0 + 4 * t;
+            if (i <= k) Rp[(k * (k + 1) >> 1) + i] = (double)r[t];
+        }
     }
-    for (int idx = tid; idx < PW * TS_LD; idx += TRINV_THREADS) Ts[idx] = 0.0;   // (lower parts stay 0)
     __syncthreads();
+    TRINV_MARK();
     // column norms of the panel, ||a_k||^2 = sum_i R(i,k)^2, four threads per column
     {
         const int k = tid >> 2, part = tid & 3;
         double s = 0.0;
-        for (int i = part; i <= k; i += 4) { const double v = Rs[k * RS_LD + i]; s += v * v; }
+        for (int i = part; i <= k; i += 4) { const double v = Rat(i, k); s += v * v; }
         s += shfl_xor_f64(s, 1);
         s += shfl_xor_f64(s, 2);
-        if (part == 0) {
-            sc[k] = pow2_scale((float)sqrt(s));
-            rinv[k] = 1.0 / (double)Rs[k * RS_LD + k];
+        if (part == 0) sc[k] = pow2_scale((float)sqrt(s));
+    }
+    TRINV_MARK();
+    // Blocked inverse with 8 x 8 blocks (16 per dimension), warp w owning block row w.
+    // (1) diagonal blocks: lane j < 8 back-substitutes column j of its block entirely in registers
+    if (lane < 8) {
+        const int o = warp * 8, j = lane;
+        double t[8];
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            double v = 0.0;
+            if (i == j) {
+                v = 1.0 / Rat(o + i, o + i);
+            } else if (i < j) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = i + 1; k < 8; ++k)
+                    if (k <= j) acc += Rat(o + i, o + k) * t[k];
+                v = -acc / Rat(o + i, o + i);
+            }
+            t[i] = v;
+            Ts[(o + i) * TS_LD + o + j] = v;                  // (zeros below the diagonal included)
         }
     }
     __syncthreads();
-    // (1) the four 32 x 32 diagonal blocks of T by back substitution, column j by the four lanes
-    // {jj, 8 + jj, 16 + jj, 24 + jj} of warp j / 8:
-    //     T(i,j) = -(sum_{k = i+1..j} R(i,k) T(k,j)) / R(i,i),   the sum split over k mod 4
+    TRINV_MARK();
+    // (2) block distance d = 1 .. 15: T(a,b) = -T(a,a) S,  S = sum_{c = a+1..b} R(a,c) T(c,b), b = a + d, on the
+    // fp64 tensor path (mma.sync.m8n8k4.f64: one 8 x 8 tile per warp).  Fragments: A[r = lane / 4][k = lane % 4],
+    // B[k = lane % 4][n = lane / 4], C[r = lane / 4][2 (lane % 4) + {0, 1}].
     {
-        const int jj = lane & 7, part = lane >> 3;
-        const int j = warp * 8 + jj;
-        const int i0 = (warp >> 2) * 32;                       // first row of this column's diagonal block
-        if (part == 0) Ts[j * TS_LD + j] = rinv[j];
-        __syncwarp();
-        for (int i = warp * 8 + 6; i >= i0; --i) {
-            double s0 = 0.0, s1 = 0.0;
-            if (i < j) {
-                int k = i + 1 + ((part - (i + 1)) & 3);      // first k > i with k = part (mod 4)
-                for (; k + 4 <= j; k += 8) {
-                    s0 += (double)Rs[k * RS_LD + i] * Ts[k * TS_LD + j];
-                    s1 += (double)Rs[(k + 4) * RS_LD + i] * Ts[(k + 4) * TS_LD + j];
+        const int fr = lane >> 2, fk = lane & 3;
+        const int a = warp;
+        for (int d = 1; d < 16; ++d) {
+            const int b = a + d;
+            if (b < 16) {
+                // (four independent accumulators: the chain of dependent DMMAs is the latency here)
+                double c2[2] = {0.0, 0.0}, c3[2] = {0.0, 0.0}, c4[2] = {0.0, 0.0}, c5[2] = {0.0, 0.0};
+                int k = 8 * (a + 1);
+                for (; k + 16 <= 8 * (b + 1); k += 16) {
+                    dmma_884(c2, Rat(8 * a + fr, k + fk), Ts[(k + fk) * TS_LD + 8 * b + fr]);
+                    dmma_884(c3, Rat(8 * a + fr, k + 4 + fk), Ts[(k + 4 + fk) * TS_LD + 8 * b + fr]);
+                    dmma_884(c4, Rat(8 * a + fr, k + 8 + fk), Ts[(k + 8 + fk) * TS_LD + 8 * b + fr]);
+                    dmma_884(c5, Rat(8 * a + fr, k + 12 + fk), Ts[(k + 12 + fk) * TS_LD + 8 * b + fr]);
                 }
-                if (k <= j) s0 += (double)Rs[k * RS_LD + i] * Ts[k * TS_LD + j];
+                if (k < 8 * (b + 1)) {                          // one 8-wide block left (d odd)
+                    dmma_884(c2, Rat(8 * a + fr, k + fk), Ts[(k + fk) * TS_LD + 8 * b + fr]);
+                    dmma_884(c3, Rat(8 * a + fr, k + 4 + fk), Ts[(k + 4 + fk) * TS_LD + 8 * b + fr]);
+                }
+                c2[0] = (c2[0] + c3[0]) + (c4[0] + c5[0]);
+                c2[1] = (c2[1] + c3[1]) + (c4[1] + c5[1]);
+                double* Sw = Sscr + warp * 64;                // S, row-major 8 x 8, private to the warp
+                *reinterpret_cast<double2*>(&Sw[fr * 8 + 2 * fk]) = make_double2(c2[0], c2[1]);
+                __syncwarp();
+                double e2[2] = {0.0, 0.0};
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    dmma_884(e2, Ts[(8 * a + fr) * TS_LD + 8 * a + 4 * h + fk], Sw[(4 * h + fk) * 8 + fr]);
+                *reinterpret_cast<double2*>(&Ts[(8 * a + fr) * TS_LD + 8 * b + 2 * fk]) = make_double2(-e2[0], -e2[1]);
             }
-            double s = s0 + s1;
-            s += shfl_xor_f64(s, 8);
-            s += shfl_xor_f64(s, 16);
-            if (part == 0 && i < j) Ts[i * TS_LD + j] = -s * rinv[i];
-            __syncwarp();
+            __syncthreads();
         }
     }
-    __syncthreads();
-    // (2) off-diagonal blocks by block distance d: T(a,b) = -T(a,a) S,  S = sum_{c = a+1..b} R(a,c) T(c,b).
-    // Dense 32-wide products, every entry independent; S is parked in the unused mirror block (b,a).
-    for (int d = 1; d < 4; ++d) {
-        const int nblk = 4 - d;                                // blocks (a, a + d), a = 0 .. 3 - d
-        for (int e = tid; e < nblk * 1024; e += TRINV_THREADS) {
-            const int a = e >> 10, b = a + d, i = (e >> 5) & 31, j = e & 31;
-            double s0 = 0.0, s1 = 0.0;
-            const float* rrow = Rs + (32 * a + i);             // R(32a + i, k) at k * RS_LD
-            const double* tcol = Ts + (32 * b + j);            // T(k, 32b + j) at k * TS_LD
-            for (int k = 32 * (a + 1); k < 32 * (b + 1); k += 2) {
-                s0 += (double)rrow[k * RS_LD] * tcol[k * TS_LD];
-                s1 += (double)rrow[(k + 1) * RS_LD] * tcol[(k + 1) * TS_LD];
-            }
-            Ts[(32 * b + i) * TS_LD + 32 * a + j] = s0 + s1;    // S(i, j) in the mirror block
-        }
-        __syncthreads();
-        for (int e = tid; e < nblk * 1024; e += TRINV_THREADS) {
-            const int a = e >> 10, b = a + d, i = (e >> 5) & 31, j = e & 31;
-            double s0 = 0.0;
-            for (int k = i; k < 32; ++k)                       // T(a,a) is upper triangular
-                s0 += Ts[(32 * a + i) * TS_LD + 32 * a + k] * Ts[(32 * b + k) * TS_LD + 32 * a + j];
-            Ts[(32 * a + i) * TS_LD + 32 * b + j] = -s0;
-        }
-        __syncthreads();
-    }
-    // T~ = diag(1/s) T, its power-of-two scale, and the two fp16 planes (column-major: k contiguous)
+    TRINV_MARK();
+    // T~ = diag(1/s) T, its power-of-two scale, and the three fp16 planes (column-major: k contiguous)
+    // Pass 1 (lanes along j: conflict-free reads of T(k, :)): T~(k,j) = T(k,j) / s_k as fp32 into a
+    // staging array laid out [j][k] (it reuses R's storage), and the largest magnitude.
+    float* stage = reinterpret_cast<float*>(Rp);             // 128 x 129 floats = exactly R's 66 048 bytes
     float mx = 0.f;
     for (int idx = tid; idx < PW * PW; idx += TRINV_THREADS) {
-        const int k = idx & (PW - 1), j = idx >> 7;
-        if (k <= j) mx = fmaxf(mx, fabsf((float)(Ts[k * TS_LD + j] * (double)(1.f / sc[k]))));
+        const int j = idx & (PW - 1), k = idx >> 7;
+        const float v = k <= j ? (float)(Ts[k * TS_LD + j] * (double)(1.f / sc[k])) : 0.f;   // exact scaling
+        stage[j * (PW + 1) + k] = v;
+        mx = fmaxf(mx, fabsf(v));
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) red[warp] = mx;
@@ -166,11 +199,10 @@ trinv128_kernel(const float* __restrict__ R, long ldr, TcApplyFactors* __restric
     mx = 0.f;
     for (int w = 0; w < TRINV_THREADS / 32; ++w) mx = fmaxf(mx, red[w]);
     const float st = pow2_scale(mx);
+    // Pass 2 (lanes along k: coalesced stores): three fp16 planes of T~ * st, column-major
     for (int idx = tid; idx < PW * PW; idx += TRINV_THREADS) {
         const int k = idx & (PW - 1), j = idx >> 7;
-        // (1 / s_k and st are powers of two: the two scalings are exact)
-        const double vd = k <= j ? Ts[k * TS_LD + j] * (double)(1.f / sc[k]) * (double)st : 0.0;
-        const float v = (float)vd;
+        const float v = stage[j * (PW + 1) + k] * st;
         const __half t1 = __float2half_rn(v);
         const float r1 = v - __half2float(t1);
         const __half t2 = __float2half_rn(r1);
@@ -180,11 +212,18 @@ trinv128_kernel(const float* __restrict__ R, long ldr, TcApplyFactors* __restric
     }
     if (tid < PW) out->colscale[tid] = sc[tid];
     if (tid == 0) out->unscale = 1.f / st;
+#ifdef LB_TRINV_TRACE
+    TRINV_MARK();
+    if (tid == 0)
+        printf("trinv cycles: load %lld norms %lld diag %lld offdiag %lld output %lld\n", tr[1] - tr[0],
+               tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int TCA_WORKERS = 256;                    // 8 warps: convert + drain
-constexpr int TCA_THREADS = TCA_WORKERS + 32;       // + 1 MMA warp
+constexpr int TCA_WORKERS = 256;                    // 8 warps: load + split + stage
+constexpr int TCA_DRAIN = 128;                      // 4 warps: TMEM -> Q (fp32) and its fp16 shadow
+constexpr int TCA_THREADS = TCA_WORKERS + 32 + TCA_DRAIN;   // warp 8 = MMA issuer
 constexpr int KB_BYTES = PW * 64 * 2;               // one 64-deep k-block of a 128-wide fp16 operand
 constexpr int PLANE_BYTES = 2 * KB_BYTES;           // K = 128: 32 KiB per plane
 constexpr int T_BYTES = 3 * PLANE_BYTES;            // t1 + t2 + t3
@@ -224,7 +263,7 @@ apply128_tc_kernel(const __grid_constant__ CUtensorMap mapT1, const __grid_const
                 mbar_init(a_full(b), TCA_WORKERS);
                 mbar_init(a_empty(b), 1);
                 mbar_init(acc_full(b), 1);
-                mbar_init(acc_empty(b), TCA_WORKERS);
+                mbar_init(acc_empty(b), TCA_DRAIN);
             }
             fence_barrier_init();
         }
@@ -287,43 +326,44 @@ apply128_tc_kernel(const __grid_constant__ CUtensorMap mapT1, const __grid_const
                 umma_commit(acc_full(b));
             }
         }
-    } else {
-        // ------------------------------------------------------------------ workers
-        if (tid < PW) colscale[tid] = fac->colscale[tid];
+    } else if (warp > 8) {
+        // ------------------------------------------------------------------ drain warps
         const float unscale = fac->unscale;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int g = tid & 15;                 // 8-row group of the tile
-        const int cbase = tid >> 4;             // columns cbase + 16 i
-        const int quad = warp & 3, half = warp >> 2;
-
-        auto drain = [&](int tile, int n) {
+        const int quad = warp & 3;              // TMEM lane quarter this warp may read
+        int n = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n) {
             const int b = n & 1;
             mbar_wait(acc_full(b), (uint32_t)(n >> 1) & 1u);
             tc_fence_after_sync();
             const int row = tile * PW + quad * 32 + lane;
             const bool row_ok = row < m;
-            const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + b * PW + half * 64;
+            const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + b * PW;
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 uint32_t d[32];
                 tmem_ld_32x32(t_addr + c * 32, d);
                 tmem_ld_wait();
                 if (row_ok) {
-                    const int col0 = half * 64 + c * 32;
-                    float* dst = A + row + (long)col0 * lda;
+                    // lanes are consecutive rows: every store instruction writes one full line
+                    float* dst = A + row + (long)(c * 32) * lda;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float v = __uint_as_float(d[j]) * unscale;
                         dst[(long)j * lda] = v;
-                        if (Qh) Qh[row + (long)(col0 + j) * ldqh] = __float2half_rn(v);
+                        if (Qh) Qh[row + (long)(c * 32 + j) * ldqh] = __float2half_rn(v);
                     }
                 }
             }
             tc_fence_before_sync();
             mbar_arrive(acc_empty(b));
-        };
-
-        int n = 0, prev_tile = -1;
+        }
+    } else {
+        // ------------------------------------------------------------------ convert warps
+        if (tid < PW) colscale[tid] = fac->colscale[tid];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int g = tid & 15;                 // 8-row group of the tile
+        const int cbase = tid >> 4;             // columns cbase + 16 i
+        int n = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n) {
             const int b = n & 1;
             mbar_wait(a_empty(b), ((uint32_t)(n >> 1) & 1u) ^ 1u);
@@ -366,10 +406,7 @@ apply128_tc_kernel(const __grid_constant__ CUtensorMap mapT1, const __grid_const
             }
             fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core
             mbar_arrive(a_full(b));
-            if (prev_tile >= 0) drain(prev_tile, n - 1);
-            prev_tile = tile;
         }
-        if (prev_tile >= 0) drain(prev_tile, n - 1);
     }
 
     tc_fence_before_sync();
