@@ -633,6 +633,10 @@ ScratchLayout scratch_layout(int m, int num_sms) {
 
 size_t panel_scratch_bytes(int m, int num_sms) { return scratch_layout(m, num_sms).total; }
 
+float* panel_colmax_scratch(void* scratch, int m, int num_sms) {
+    return reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + scratch_layout(m, num_sms).colmax_off);
+}
+
 cudaError_t panel_init() {
     cudaError_t e = cudaFuncSetAttribute(apply128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(ApplySmem));
@@ -665,7 +669,7 @@ int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_
 }
 
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
-                        long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc) {
+                        long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc, bool colmax_ready) {
     const ScratchLayout L = scratch_layout(m, num_sms);
     uint8_t* base = static_cast<uint8_t*>(scratch);
     double* part = reinterpret_cast<double*>(base + L.part_off);
@@ -677,8 +681,8 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
     cudaError_t le;
     if (panel_uses_i8_gram(m, num_sms, A, lda, allow_tc)) {
         ggrid = panel_gram_i8_grid(m, num_sms);
-        if ((le = panel_gram_i8(stream, num_sms, m, A, lda, reinterpret_cast<float*>(base + L.colmax_off), part,
-                                info + 1)) != cudaSuccess)
+        if ((le = panel_gram_i8(stream, num_sms, m, A, lda, reinterpret_cast<float*>(base + L.colmax_off),
+                                colmax_ready, part, info + 1)) != cudaSuccess)
             return le;
     } else if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream,
                                 (const float*)A, lda, m, part)) != cudaSuccess) {

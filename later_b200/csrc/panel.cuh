@@ -27,8 +27,10 @@ size_t panel_scratch_bytes(int m, int num_sms);
 // apply (panel_tc.cu), whose Q is accurate to ~1e-6 instead of ~1e-7: the recursion, which consumes
 // Q rounded to fp16 anyway, says yes; the stand-alone panel entry point, which replaces the
 // reference's all-fp32 panel, says no.
+// colmax_ready: panel_colmax_scratch() already holds this panel's column maxima.
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
-                        long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc);
+                        long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc,
+                        bool colmax_ready = false);
 
 cudaError_t panel_init();
 // Which apply panel_qr128 will use (4 launches per panel with forward substitution, 5 with the
@@ -56,9 +58,12 @@ cudaError_t tc_apply_init();
 int panel_gram_i8_grid(int m, int num_sms);
 bool panel_gram_i8_fits(int m, int num_sms);
 // colmax_part: kColmaxParts floats of scratch per column (written by the kernel's own first pass).
-constexpr int kColmaxParts = 64;
+constexpr int kColmaxParts = 160;   // >= the grid of any kernel that fills them (colmax128: 64, update: <= SMs)
+// colmax_ready: the partials were already written by the update kernel that produced the panel.
 cudaError_t panel_gram_i8(cudaStream_t stream, int num_sms, int m, const float* A, long lda,
-                          float* colmax_part, double* part, int* info);
+                          float* colmax_part, bool colmax_ready, double* part, int* info);
+// Where in a panel scratch area (panel_scratch_bytes(m, num_sms)) the column-maxima partials live.
+float* panel_colmax_scratch(void* scratch, int m, int num_sms);
 // Q = A R^-1 for an m x 128 panel whose R (fp32, upper triangular) is already in place; needs
 // lda % 4 == 0 and a 16-byte aligned A.
 cudaError_t panel_apply_tc(cudaStream_t stream, int num_sms, int m, float* A, long lda, const float* R,

@@ -454,7 +454,7 @@ colmax128_kernel(const float* __restrict__ A, long lda, int m, float* __restrict
     pdl_wait();
     const float* src = A + (long)c * lda;
     float mx = 0.f;
-    for (int i = (blockIdx.x * 256 + threadIdx.x) * 4; i < m; i += kColmaxParts * 256 * 4) {
+    for (int i = (blockIdx.x * 256 + threadIdx.x) * 4; i < m; i += gridDim.x * 256 * 4) {
         const float4 v = *reinterpret_cast<const float4*>(src + i);      // m % 8 == 0, aligned
         mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
     }
@@ -465,6 +465,8 @@ colmax128_kernel(const float* __restrict__ A, long lda, int m, float* __restrict
         for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
         colmax_part[c * kColmaxParts + blockIdx.x] = mx;
     }
+    if (blockIdx.x == 0)       // slots no block of this grid owns
+        for (int sidx = gridDim.x + threadIdx.x; sidx < kColmaxParts; sidx += 256) colmax_part[c * kColmaxParts + sidx] = 0.f;
 }
 
 __global__ void __launch_bounds__(GI8_THREADS, 1)
@@ -653,9 +655,10 @@ bool panel_gram_i8_fits(int m, int num_sms) {
 }
 
 cudaError_t panel_gram_i8(cudaStream_t stream, int num_sms, int m, const float* A, long lda,
-                          float* colmax_part, double* part, int* info) {
-    cudaError_t e = launch_pdl(colmax128_kernel, dim3(kColmaxParts, PW), dim3(256), 0, stream, A, lda, m,
-                               colmax_part);
+                          float* colmax_part, bool colmax_ready, double* part, int* info) {
+    cudaError_t e = cudaSuccess;
+    if (!colmax_ready)
+        e = launch_pdl(colmax128_kernel, dim3(64, PW), dim3(256), 0, stream, A, lda, m, colmax_part);
     if (e != cudaSuccess) return e;
     e = launch_pdl(gram128_i8_kernel, dim3(panel_gram_i8_grid(m, num_sms)), dim3(GI8_THREADS),
                    (size_t)GI8_SMEM, stream, A, lda, m, (const float*)colmax_part, part, info);

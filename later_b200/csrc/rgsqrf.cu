@@ -197,6 +197,7 @@ struct Recursion {
     CUtensorMap q128, q256, q64;
     cudaError_t err = cudaSuccess;
     long launches = 0;
+    int colmax_col = -1;    // first column of the panel whose column maxima the last update left behind
 
     void check(cudaError_t e) {
         if (err == cudaSuccess && e != cudaSuccess) err = e;
@@ -206,10 +207,13 @@ struct Recursion {
         if (err != cudaSuccess) return;
         cudaStream_t st = ctx->stream;
         if (w <= NMIN) {
+            const bool ready = colmax_col == c0;
+            colmax_col = -1;
             check(panel_qr128(st, ctx->num_sms, p->m, p->A + (long)c0 * p->lda, p->lda,
                               p->R + c0 + (long)c0 * p->ldr, p->ldr, p->Qh + (long)c0 * p->ldh,
-                              p->ldh, p->panel_scratch, true));
-            launches += panel_launch_count(p->m, ctx->num_sms, p->A + (long)c0 * p->lda, p->lda, true);
+                              p->ldh, p->panel_scratch, true, ready));
+            launches += panel_launch_count(p->m, ctx->num_sms, p->A + (long)c0 * p->lda, p->lda, true) -
+                        (ready ? 1 : 0);
         } else {
             qr(c0, w / 2);
             node_tail(c0, w);
@@ -242,9 +246,19 @@ struct Recursion {
         HalfMatrix rm{p->R12h, h, nb, h};
         const int ubn = nb % 256 == 0 ? update_bn(h) : 128;
         check(make_tensor_map_f16(&r12map, rm, 64, ubn));
+        colmax_col = -1;
         if (update_uses_tma(h) && p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
+            // columns cb .. cb + 127 are the next panel: if it will use the integer Gram kernel, this
+            // update leaves their maxima behind and saves that kernel its first pass over the panel
+            // (worth its ~2 % of epilogue work only when that pass would come from HBM: a panel that
+            // still sits in the 126 MB L2 after this update is scanned in ~10 us)
+            const bool want = panel_uses_i8_gram(p->m, ctx->num_sms, p->A + (long)cb * p->lda, p->lda, true) &&
+                              (size_t)p->m * kPanelWidth * sizeof(float) > ((size_t)96 << 20);
             check(tc_update_tma(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, nb, p->A, p->m,
-                                p->n, p->lda, cb, p->Qh, p->ldh, true));
+                                p->n, p->lda, cb, p->Qh, p->ldh, true,
+                                want ? panel_colmax_scratch(p->panel_scratch, p->m, ctx->num_sms) : nullptr,
+                                kColmaxParts));
+            if (want) colmax_col = cb;
         } else {   // (TMA also needs 16-byte aligned column strides)
             check(tc_update(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, nb,
                             p->A + (long)cb * p->lda, p->lda, p->Qh + (long)cb * p->ldh, p->ldh, true));

@@ -100,10 +100,12 @@ cudaError_t tc_update_init();
 // C block = Cmat(row0:row0+Mr, c_c0:c_c0+Nc) (-)= Qh(row0:row0+Mr, colA:colA+K) * Bh(:, colB0:colB0+Nc).
 // Cmat is the whole column-major fp32 matrix (c_rows x c_cols, ld ldc); with sub=true the fp16
 // shadow of the new C block goes to the same coordinates of Hmat (ld ldh).  Nc must be a multiple
-// of bn unless the block ends at the matrix edge.
+// of bn unless the block ends at the matrix edge.  colmax_part (sub only, optional): per-CTA partial
+// maxima of |new C| over the block's first 128 columns, [col][colmax_parts] floats, every slot written.
 cudaError_t tc_update_tma(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_64,
                           const CUtensorMap& mapB_bn, int bn, int row0, int Mr, int colA, int K,
                           int colB0, int Nc, float* Cmat, long c_rows, long c_cols, long ldc, int c_c0,
-                          __half* Hmat, long ldh, bool sub);
+                          __half* Hmat, long ldh, bool sub, float* colmax_part = nullptr,
+                          int colmax_parts = 0);
 
 }  // namespace lb

@@ -37,7 +37,7 @@ struct UCfg {
     static constexpr int C16_BYTES = BM * CCH * 2;
     static constexpr int CSLOT_BYTES = C32_BYTES + C16_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 1024;     // barriers (< 256 B) + 128 column maxima
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSLOTS * CSLOT_BYTES + BAR_BYTES + 1024;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -49,6 +49,11 @@ struct UpdParams {
     int a_c0, a_c1;   // A operand origin (row, col) in the fp16 shadow
     int b_c1;         // first column of B (R12h / Wh) to use
     int c_r0, c_c0;   // C origin (row, col) in the fp32 matrix (and in the fp16 shadow)
+    // Optional: largest |value| written to each of the first 128 columns of the C block, as one
+    // partial per CTA, colmax_part[col * colmax_parts + blockIdx.x] (slots >= gridDim.x zeroed).
+    // These columns are the next panel; its integer Gram kernel scales by them (panel_tc.cu).
+    float* colmax_part;
+    int colmax_parts;
 };
 
 __device__ __forceinline__ void tile_coords_u(int t, int tiles_m, int tiles_n, int& m_blk,
@@ -192,6 +197,11 @@ tc_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int quad = warp & 3;
         const int r = quad * 32 + lane;          // row inside the tile = TMEM lane
         const bool leader = (warp == 4 && lane == 0);
+        unsigned* cmax = reinterpret_cast<unsigned*>(smem_gen + (bar_base - smem_base) + 256);
+        if (p.colmax_part) {
+            cmax[r] = 0u;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         int acc = 0;
         uint32_t acc_phase = 0;
         int slot = 0;
@@ -219,12 +229,30 @@ tc_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
                 tmem_ld_wait();
+                const bool track = p.colmax_part && n_blk == 0 && c * CCH < 128;   // warp-uniform
 #pragma unroll
                 for (int j = 0; j < CCH; ++j) {
                     const float dv = __uint_as_float(d[j]);
                     const float v = SUB ? sc[j * BM + r] - dv : dv;
                     sc[j * BM + r] = v;
                     if (SHADOW) sh[j * BM + r] = __float2half_rn(v);
+                    if (track) d[j] = __float_as_uint(fabsf(v));   // (ordered like unsigned integers)
+                }
+                if (track) {
+                    // Column maxima over this warp's 32 rows for all CCH columns at once: recursive
+                    // halving, lane L ends up with column L (mod CCH) - CCH - 1 shuffles, not 5 CCH.
+#pragma unroll
+                    for (int half = CCH / 2; half >= 1; half >>= 1) {
+                        const bool upper = (lane & half) != 0;
+#pragma unroll
+                        for (int i = 0; i < half; ++i) {
+                            const uint32_t send = upper ? d[i] : d[i + half];
+                            const uint32_t keep = upper ? d[i + half] : d[i];
+                            d[i] = max(keep, __shfl_xor_sync(0xffffffffu, send, half));
+                        }
+                    }
+                    if (CCH == 16) d[0] = max(d[0], __shfl_xor_sync(0xffffffffu, d[0], 16));
+                    if (lane < CCH) atomicMax(&cmax[c * CCH + lane], d[0]);
                 }
                 fence_proxy_async_smem();
                 asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps
@@ -251,6 +279,13 @@ tc_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (leader) {
             tma_store_wait<0>();
             // (remaining c_empty arrivals are irrelevant: the producer has finished)
+        }
+        if (p.colmax_part) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float* dst = p.colmax_part + (long)r * p.colmax_parts;
+            dst[blockIdx.x] = __uint_as_float(cmax[r]);
+            if (blockIdx.x == 0)
+                for (int sidx = gridDim.x; sidx < p.colmax_parts; ++sidx) dst[sidx] = 0.f;
         }
     }
 
@@ -330,8 +365,10 @@ cudaError_t tc_update_init() {
 cudaError_t tc_update_tma(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_64,
                           const CUtensorMap& mapB_bn, int bn, int row0, int Mr, int colA, int K,
                           int colB0, int Nc, float* Cmat, long c_rows, long c_cols, long ldc, int c_c0,
-                          __half* Hmat, long ldh, bool sub) {
+                          __half* Hmat, long ldh, bool sub, float* colmax_part, int colmax_parts) {
     UpdParams p{};
+    p.colmax_part = sub ? colmax_part : nullptr;
+    p.colmax_parts = colmax_parts;
     p.M = Mr; p.N = Nc;
     p.kb_total = (K + BK - 1) / BK;
     p.tiles_m = (Mr + BM - 1) / BM;

@@ -207,7 +207,7 @@ def test_integer_gram_vs_fp64_gram(qr, m, n, dist, monkeypatch):
         out[i8] = (A, R, c.last_launch_count)
         c.close()
     (Q0, R0, l0), (Q1, R1, l1) = out["0"], out["1"]
-    assert l1 == l0 + n // 128                                   # one more launch per panel (column maxima)
+    assert l0 < l1 <= l0 + n // 128     # column maxima: own pass for the first panel, else from the update
     assert (R1 - R0).abs().max().item() <= 5e-6 * R0.abs().max().item()
     # (a last-bit change of R12 can flip fp16 roundings of the update's operands: Q moves at that level)
     assert (Q1 - Q0).abs().max().item() <= 4.9e-4 * Q0.abs().max().item()
