@@ -6,12 +6,16 @@
 //   * operands of the two products are fp16 exactly as in the reference (RN cast of Q1, A2 and of
 //     R12), but the casts are fused into the producers: the panel kernel and the update kernel
 //     write an fp16 shadow of every column they finalise, the gram kernel emits fp16 R12 from its
-//     epilogue.  The reference's three s2h passes per node (util/util.cu:24-32) disappear; one
-//     initial cast of A remains.
-//   * the products are hand-written tcgen05 kernels (tc_gemm.cu), not cublasGemmEx.
-//   * the base case is one Gram/Cholesky panel (panel.cu), not the 26-launch CAQR chain.
-//   * the whole launch sequence (~1 000 launches for 16384^2) is captured once into a CUDA graph
-//     and replayed; the reference serialises ~4 000 launches on the legacy stream.
+//     epilogue.  The reference's three s2h passes per node (util/util.cu:24-32) disappear; the
+//     caller's input columns are cast once, by the left-spine node that first reads them.
+//   * the products are hand-written tcgen05 kernels (tc_gemm.cu, tc_update.cu), not cublasGemmEx.
+//   * the base case is one Gram/Cholesky panel (panel.cu; tensor-core kernels of panel_tc.cu for
+//     tall panels), not the 26-launch CAQR chain.
+//   * the whole launch sequence (893 launches for 16384^2) is captured into a CUDA graph on the
+//     second identical call and replayed; the reference serialises ~4 000 launches on the legacy
+//     stream.
+//   * the host entry point runs the same operations left-looking over column pieces so that the
+//     PCIe transfers stream underneath (HostPipe below).
 #include "../../include/later_b200.h"
 
 #include <algorithm>
