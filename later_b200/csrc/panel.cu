@@ -654,7 +654,9 @@ bool panel_uses_i8_gram(int m, int num_sms, const float* A, long lda, bool allow
     const char* s = getenv("LB_GRAM_I8");
     if (s && atoi(s) == 0) return false;
     const bool aligned = lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
-    return allow_tc && aligned && m >= kTcApplyMinRows && panel_gram_i8_fits(m, num_sms);
+    int min_rows = kI8GramMinRows;
+    if (const char* t = getenv("LB_GRAM_I8_MIN_ROWS")) min_rows = atoi(t);
+    return allow_tc && aligned && m >= min_rows && panel_gram_i8_fits(m, num_sms);
 }
 
 bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc) {

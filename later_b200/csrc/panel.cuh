@@ -43,6 +43,8 @@ int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_
 // Rows from which panel_qr128 switches from the fp32 forward-substitution apply (hidden behind the
 // Cholesky kernel on short panels) to the split-precision tcgen05 apply (HBM-bound).
 constexpr int kTcApplyMinRows = 65536;
+// Rows from which the Gram matrix is formed on the integer tensor path instead of DMMA.
+constexpr int kI8GramMinRows = 65536;
 
 struct TcApplyFactors {
     // three fp16 planes t1 + t2 + t3 = fp32(diag(1/s) R^-1) * 2^e exactly, column-major
