@@ -50,9 +50,9 @@ size_t later_b200_workspace_bytes(const later_b200_ctx* ctx, int m, int n);
 int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr);
 
 /* Same with HOST buffers (what the reference's driver does by hand, test/test_qr.cu:47-56): A goes
- * to the device in doubling column pieces, each left-spine node of the recursion starting as soon
- * as its columns have arrived; every block of R and every max(128, n/16) columns of Q travel back
- * the moment they are final, while the factorisation continues.  hA <- Q.  hR receives its block
+ * to the device in column pieces of width max(128, n/16) and is factored left-looking, piece by
+ * piece, as it arrives; every piece of Q and its columns of R travel back the moment they are
+ * final, while the factorisation continues.  hA <- Q.  hR receives its block
  * upper triangle at that granularity (strictly lower entries inside the diagonal blocks are
  * written as zero); the blocks below are NOT written - they are zero by definition and the
  * reference never writes them either.  Page-locked buffers are needed for the overlap (and for
