@@ -24,6 +24,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
 SOURCES = {
     "tc_gemm.cu": [],
     "tc_update.cu": [],
+    "tc_gram_cast.cu": [],
     "panel.cu": [],
     "panel_tc.cu": [],
     "rgsqrf.cu": [],

@@ -236,15 +236,29 @@ struct Recursion {
     // The recursion calls it with A2 = the whole right half of node (c0, 2h); the left-looking
     // host schedule with one piece of it.  The split-K factor is always the one of the whole node,
     // so that both orders add the same partial sums in the same order.
-    void gram_update(int c0, int h, int cb, int nb, bool zero_mirror) {
+    // b_is_input: A2 is still the caller's fp32 input - no kernel has written its fp16 shadow yet.
+    // Tall (bandwidth-bound) products then round it to fp16 inside the Gram kernel's load path
+    // (tc_gram_cast.cu); otherwise the shadow is made first.
+    void gram_update(int c0, int h, int cb, int nb, bool zero_mirror, bool b_is_input) {
         if (err != cudaSuccess) return;
         cudaStream_t st = ctx->stream;
         const int bn = nb % 256 == 0 ? gram_bn(h) : 128;
         const int splits = choose_gram_splits(ctx->num_sms, h, h, gram_bn(h), p->m);
+        float* R12 = p->R + c0 + (long)cb * p->ldr;
         // (the mirror block R21, which the algorithm never produces, is written as zero on the way)
-        check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, cb, nb,
-                      p->R + c0 + (long)cb * p->ldr, p->ldr, p->R12h, h, p->part, splits,
-                      zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr));
+        float* Z = zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr;
+        const char* fv = getenv("LB_GRAM_CAST");      // 0: always cast first (tests, profiling)
+        const bool fuse_ok = !fv || atoi(fv) != 0;
+        const bool fused = b_is_input && fuse_ok && splits >= 2 && p->m >= kTcApplyMinRows && p->lda % 4 == 0 &&
+                           (reinterpret_cast<uintptr_t>(p->A) & 15) == 0;
+        if (fused) {
+            check(tc_gram_cast(st, ctx->num_sms, q128, bn, p->m, c0, h, p->A + (long)cb * p->lda, p->lda, nb,
+                               R12, p->ldr, p->R12h, h, p->part, splits, Z));
+        } else {
+            if (b_is_input) cast(cb, cb + nb);
+            check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, cb, nb, R12,
+                          p->ldr, p->R12h, h, p->part, splits, Z));
+        }
         launches += splits > 1 ? 2 : 1;
         CUtensorMap r12map;
         HalfMatrix rm{p->R12h, h, nb, h};
@@ -276,12 +290,15 @@ struct Recursion {
         for (int j = 0; j < pieces && err == cudaSuccess; ++j) {
             const int cj = j * P;
             pipe->need(cj + P);
-            // piece 0 is cast by the left spine of its own recursion; later pieces are read by a Gram
-            // product before anything has updated them
-            if (j > 0) cast(cj, cj + P);
+            // (piece 0 is cast by the left spine of its own recursion; a later piece is the caller's
+            // input until the first - widest - of these updates has run)
+            bool fresh = j > 0;
             for (int s = pieces; s >= 2; s /= 2) {
                 const int a = j / s * s;            // node (a, s) in pieces; j in its right half?
-                if (j - a >= s / 2) gram_update(a * P, s / 2 * P, cj, P, false);
+                if (j - a >= s / 2) {
+                    gram_update(a * P, s / 2 * P, cj, P, false, fresh);
+                    fresh = false;
+                }
             }
             qr(cj, P);
             // R stays on the device: its blocks below this piece's diagonal block, which no Gram
@@ -297,10 +314,9 @@ struct Recursion {
     void node_tail(int c0, int w) {
         if (err != cudaSuccess) return;
         const int h = w / 2;
-        // Left spine: A2 is still the caller's input, so its fp16 shadow is made here (everywhere
-        // else the update that last wrote A2 has refreshed it).
-        if (c0 == 0) cast(h, w);
-        gram_update(c0, h, c0 + h, h, true);
+        // Left spine (c0 == 0): A2 is still the caller's input; everywhere else the update that last
+        // wrote A2 has refreshed its fp16 shadow.
+        gram_update(c0, h, c0 + h, h, true, c0 == 0);
         qr(c0 + h, h);
     }
 };
@@ -516,6 +532,7 @@ int later_b200_create(later_b200_ctx** out, int device, void* stream) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
     cudaError_t e = tc_gemm_init();
+    if (e == cudaSuccess) e = tc_gram_cast_init();
     if (e == cudaSuccess) e = tc_update_init();
     if (e == cudaSuccess) e = panel_init();
     if (e != cudaSuccess) {

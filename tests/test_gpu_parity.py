@@ -214,6 +214,29 @@ def test_integer_gram_vs_fp64_gram(qr, m, n, dist, monkeypatch):
     assert qr.orthogonality(Q1) <= 1.1 * qr.orthogonality(Q0) + 1e-8
 
 
+@pytest.mark.parametrize("m,n", [(65536, 256), (131072, 1024), (70008, 512)])
+def test_cast_fused_into_gram_load_is_bit_identical(qr, m, n, monkeypatch):
+    """Left-spine Gram products of tall matrices read the caller's fp32 columns and round them to fp16
+    inside the kernel's load path (tc_gram_cast.cu) instead of running the cast kernel first: same
+    rounding, same split-K factor, same accumulation order - same bits, one launch less per node."""
+    g = torch.Generator(device="cuda").manual_seed(23)
+    A0 = torch.randn(m, n, device="cuda", generator=g)
+    out = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("LB_GRAM_CAST", fused)
+        c = qr.Context()
+        A = qr.to_colmajor(A0)
+        R = qr.colmajor_empty(n, n)
+        R.fill_(float("nan"))
+        qr.later_rgsqrf(c, m, n, A, m, R, n)
+        torch.cuda.synchronize()
+        out[fused] = (A, R, c.last_launch_count)
+        c.close()
+    (Q0, R0, l0), (Q1, R1, l1) = out["0"], out["1"]
+    assert torch.equal(R0, R1) and torch.equal(Q0, Q1)
+    assert l1 < l0
+
+
 # ------------------------------------------------------------------------------ full-size properties
 def _factor_device(qr, ctx, A0: torch.Tensor):
     m, n = A0.shape
