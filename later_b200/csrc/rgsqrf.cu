@@ -249,10 +249,11 @@ struct Recursion {
         float* Z = zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr;
         const char* fv = getenv("LB_GRAM_CAST");      // 0: always cast first (tests, profiling)
         const bool fuse_ok = !fv || atoi(fv) != 0;
-        const bool fused = b_is_input && fuse_ok && splits >= 2 && p->m >= kTcApplyMinRows && p->lda % 4 == 0 &&
+        const bool fused = b_is_input && fuse_ok && splits >= 2 && tc_gram_cast_supports(h) &&
+                           p->m >= kTcApplyMinRows && p->lda % 4 == 0 &&
                            (reinterpret_cast<uintptr_t>(p->A) & 15) == 0;
         if (fused) {
-            check(tc_gram_cast(st, ctx->num_sms, q128, bn, p->m, c0, h, p->A + (long)cb * p->lda, p->lda, nb,
+            check(tc_gram_cast(st, ctx->num_sms, q128, p->m, c0, h, p->A + (long)cb * p->lda, p->lda, nb,
                                R12, p->ldr, p->R12h, h, p->part, splits, Z));
         } else {
             if (b_is_input) cast(cb, cb + nb);

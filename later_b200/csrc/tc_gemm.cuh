@@ -95,9 +95,11 @@ int choose_gram_splits(int num_sms, int Mc, int Nc, int bn, int k_rows);
 // Split-K Gram product with the B operand taken from an fp32 matrix and rounded to fp16 on the way
 // into shared memory (tc_gram_cast.cu): C[Mc x Nc] = Qh(:, colA:colA+Mc)^T * fp16(B[k_rows x Nc]).
 // Same splits, same accumulation order and therefore the same bits as cast + tc_gram.  splits >= 2.
-cudaError_t tc_gram_cast(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int bn, int k_rows,
+// Mc must be 128, 256 or 512 (tc_gram_cast_supports): one CTA holds all Mc / 128 row tiles.
+cudaError_t tc_gram_cast(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int k_rows,
                          int colA, int Mc, const float* B, long ldb, int Nc, float* C, long ldc, __half* Ch,
                          long ldch, float* part, int splits, float* Z);
+bool tc_gram_cast_supports(int Mc);
 cudaError_t tc_gram_cast_init();
 
 // Sets the dynamic shared-memory limits of all kernel instantiations (once per device).
