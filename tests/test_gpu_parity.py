@@ -316,7 +316,8 @@ def _host_block_mask(n):
 
 @pytest.mark.parametrize("m,n,pinned,pad", [(1024, 256, True, 0), (1024, 128, True, 0),
                                             (4096, 2048, True, 0), (8192, 4096, True, 0),
-                                            (2048, 512, False, 0), (2048, 512, True, 24)])
+                                            (2048, 512, False, 0), (2048, 512, True, 24),
+                                            (65544, 256, True, 8)])    # tall: tensor-core panel kernels
 def test_host_entry_point_matches_device_entry_point(qr, ctx, m, n, pinned, pad):
     """Same bits as the device entry point, on the first (direct), second (graph capture) and third
     (graph replay) call; entries below the block diagonal of hR are left alone."""
@@ -373,6 +374,23 @@ def test_leading_dimensions_are_honoured(qr, ctx):
     R = qr.colmajor_empty(256, 256, ld=300)
     qr.later_rgsqrf(ctx, 512, 256, A, 520, R, 300)
     assert np.array_equal(A.cpu().numpy(), Q1) and np.array_equal(R.cpu().numpy(), R1)
+
+
+def test_leading_dimensions_are_honoured_on_the_tall_path(qr, ctx):
+    """Same with the tensor-core panel kernels and the cast-fused Gram product (m >= 65536), a row
+    count that is not a multiple of 128 and leading dimensions that are not the row count."""
+    m, n = 65544, 512
+    g = torch.Generator(device="cuda").manual_seed(24)
+    A0 = torch.randn(m, n, device="cuda", generator=g)
+    A1 = qr.to_colmajor(A0)
+    R1 = qr.colmajor_empty(n, n)
+    qr.later_rgsqrf(ctx, m, n, A1, m, R1, n)
+    A2 = qr.colmajor_empty(m, n, ld=m + 40)
+    A2.copy_(A0)
+    R2 = qr.colmajor_empty(n, n, ld=n + 12)
+    qr.later_rgsqrf(ctx, m, n, A2, m + 40, R2, n + 12)
+    assert torch.equal(A1, A2) and torch.equal(R1, R2)
+    assert qr.backward_error(A0, A2, R2) <= 1e-4 and qr.orthogonality(A2) <= 1e-5
 
 
 def test_argument_errors_do_not_launch(qr, ctx):
