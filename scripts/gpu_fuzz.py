@@ -6,13 +6,14 @@ from later_b200 import qr
 torch.backends.cuda.matmul.allow_tf32 = False
 seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
+kinds = sys.argv[3].split(",") if len(sys.argv) > 3 else ["short", "mid", "tall"]
 rng = random.Random(seed)
 ctx = qr.Context()
 t_end = time.time() + budget
 cases = fails = 0
 while time.time() < t_end:
     n = 128 << rng.randrange(0, 5)                      # 128 .. 2048
-    kind = rng.choice(["short", "mid", "tall"])
+    kind = rng.choice(kinds)
     lo, hi = {"short": (n, 4 * n), "mid": (4 * n, 65536), "tall": (65536, 400000)}[kind]
     lo = max(lo, n)
     if hi <= lo: hi = lo + 8
