@@ -25,8 +25,10 @@
 //                       integer is cut into four balanced base-256 digits (one XOR-ADD pair: the
 //                       digits are the bytes of (x + 0x00808080) ^ 0x00808080), and the digit planes
 //                       D_s are multiplied with tcgen05.mma kind::i8 into four int32 TMEM accumulators,
-//                       one per weight 256^(s+t), s + t = 3 .. 6 (10 of the 16 plane pairs; the six
-//                       dropped pairs are below 2^-26 of a product).  Integer accumulation is exact,
+//                       one per weight 256^(s+t), s + t = 3 .. 6 (the six pairs with s + t < 3 are below
+//                       2^-26 of a product and dropped; of the other ten, three are transposes of
+//                       pairs already computed and are recovered when the accumulators are drained:
+//                       7 pairs = 28 MMAs per 128-row tile).  Integer accumulation is exact,
 //                       so the result does not depend on summation order; the accumulators are read
 //                       ONCE per CTA, recombined and unscaled in fp64, and handed to the same
 //                       fixed-order reduce + fp64 Cholesky as the DMMA Gram kernel of panel.cu.  That
@@ -521,6 +523,9 @@ gram128_i8_kernel(const float* __restrict__ A, long lda, int m, const float* __r
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         if (s + t < 3) continue;           // weight 256^(s+t): below 2^-26 of a product
+                        // D_t^T D_s = (D_s^T D_t)^T: the groups made of such mirror pairs only (s + t = 3
+                        // and 5) get one of each and are symmetrised when the accumulators are drained
+                        if (s > t && ((s + t) & 1)) continue;
                         const uint64_t a_desc = make_smem_desc_sw128(buf + s * DIGIT_PLANE_BYTES, 16, 1024);
                         const uint64_t b_desc = make_smem_desc_sw128(buf + t * DIGIT_PLANE_BYTES, 16, 1024);
                         // the first pair of every group in issue order: (0,3), (1,3), (2,3), (3,3)
@@ -602,24 +607,44 @@ gram128_i8_kernel(const float* __restrict__ A, long lda, int m, const float* __r
         }
         if (overflow) atomicOr(info, 2);        // (Inf / NaN in the panel)
 
-        // ---- drain: G(j,k) 2^(E_j + E_k) = sum_g acc_g(j,k) 256^(g+3), upper 32 x 32 blocks only
+        // ---- drain: G(j,k) 2^(E_j + E_k) = sum_g acc_g(j,k) 256^(g+3), upper 32 x 32 blocks only.
+        // Groups 0 and 2 (s + t = 3, 5) hold one pair of each mirror couple: X = acc_0 256^3 + acc_2 256^5
+        // (exact in fp64: 47 bits) is staged in shared memory (the digit buffers, now free; 128 x 128
+        // doubles, XOR-swizzled so that row writes and column reads are both conflict-free) and
+        // G gets X + X^T.
         mbar_wait(acc_done, 0);
         tc_fence_after_sync();
         const int quad = warp & 3, half = warp >> 2;
         const int j = quad * 32 + lane;
+        double* X = reinterpret_cast<double*>(smem_gen);
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+            const int k0 = (2 * half + cc) * 32;
+            uint32_t d0[32], d2[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + 0 * PW + k0, d0);
+            tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + 2 * PW + k0, d2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                X[j * PW + ((k0 + i) ^ (j & 31))] =
+                    fma((double)(int)d2[i], 1099511627776.0 /* 256^5 */, (double)(int)d0[i] * 16777216.0 /* 256^3 */);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const double uj = unscale[j];
         double* dst_cta = part + (long)blockIdx.x * G_ELEMS;
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
             const int bj = 2 * half + cc;
             if (bj < quad) continue;                // strictly lower block: never read
+            const int k0 = bj * 32;
             double sum[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sum[i] = 0.0;
+            for (int i = 0; i < 32; ++i)
+                sum[i] = X[j * PW + ((k0 + i) ^ (j & 31))] + X[(k0 + i) * PW + (j ^ ((k0 + i) & 31))];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 1; g < 4; g += 2) {        // the complete groups: s + t = 4 and 6
                 uint32_t d[32];
-                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + g * PW + bj * 32, d);
+                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + g * PW + k0, d);
                 tmem_ld_wait();
                 const double wgt = (double)(1ull << (8 * (g + 3)));
 #pragma unroll
@@ -629,7 +654,7 @@ gram128_i8_kernel(const float* __restrict__ A, long lda, int m, const float* __r
 #pragma unroll
             for (int i = 0; i < 32; i += 2)
                 *reinterpret_cast<double2*>(dst + i) =
-                    make_double2(sum[i] * uj * unscale[bj * 32 + i], sum[i + 1] * uj * unscale[bj * 32 + i + 1]);
+                    make_double2(sum[i] * uj * unscale[k0 + i], sum[i + 1] * uj * unscale[k0 + i + 1]);
         }
     }
     tc_fence_before_sync();
