@@ -556,54 +556,69 @@ gram128_i8_kernel(const float* __restrict__ A, long lda, int m, const float* __r
         const int q = tid & 7;                  // 16-row chunk of the tile
         const int cb = tid >> 3;                // columns cb + 32 u
         bool overflow = false;
-        int n = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n) {
+        // this thread's four chunks (16 rows x 1 column each) of a tile: 16 loads in flight at once
+        auto issue = [&](int tile, float4 (&v)[4][4]) {
+            const int row0 = tile * PW + q * 16;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* src = A + row0 + (long)(cb + 32 * u) * lda;
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    v[u][w] = row0 + 4 * w < m ? *reinterpret_cast<const float4*>(src + 4 * w)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        // One pipeline step: put the NEXT tile's loads in flight (second register buffer), then
+        // convert the current one - with a single buffer every tile paid the full DRAM latency
+        // (measured 2.9 us per tile where the 28 MMAs need 1.75 and the 64 KB of HBM traffic 1.45).
+        auto step = [&](int tile, int n, float4 (&cur)[4][4], float4 (&nxt)[4][4]) {
+            if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x, nxt);
             const int b = n & 1;
             mbar_wait(a_empty(b), ((uint32_t)(n >> 1) & 1u) ^ 1u);
             uint8_t* buf = smem_gen + b * DIGIT_BUF_BYTES;
-            const int row0 = tile * PW + q * 16;
-            {   // this thread's four chunks (16 rows x 1 column each), all 16 loads in flight at once
-                float4 v[4][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float* src = A + row0 + (long)(cb + 32 * u) * lda;
+            for (int u = 0; u < 4; ++u) {
+                const int c = cb + 32 * u;
+                const float s = scale[c];
+                uint32_t pl[4][4];           // [digit plane][word of 4 consecutive rows]
 #pragma unroll
-                    for (int w = 0; w < 4; ++w)
-                        v[u][w] = row0 + 4 * w < m ? *reinterpret_cast<const float4*>(src + 4 * w)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int w = 0; w < 4; ++w) {
+                    const float f[4] = {cur[u][w].x * s, cur[u][w].y * s, cur[u][w].z * s, cur[u][w].w * s};
+                    uint32_t z[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c = cb + 32 * u;
-                    const float s = scale[c];
-                    uint32_t pl[4][4];           // [digit plane][word of 4 consecutive rows]
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const float f[4] = {v[u][w].x * s, v[u][w].y * s, v[u][w].z * s, v[u][w].w * s};
-                        uint32_t z[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            overflow |= fabsf(f[i]) > 1073741824.f;
-                            // balanced base-256 digits = bytes of (x + 0x00808080) ^ 0x00808080
-                            z[i] = ((uint32_t)__float2int_rn(f[i]) + 0x00808080u) ^ 0x00808080u;
-                        }
-                        const uint32_t lo01 = __byte_perm(z[0], z[1], 0x5140), lo23 = __byte_perm(z[2], z[3], 0x5140);
-                        const uint32_t hi01 = __byte_perm(z[0], z[1], 0x7362), hi23 = __byte_perm(z[2], z[3], 0x7362);
-                        pl[0][w] = __byte_perm(lo01, lo23, 0x5410);
-                        pl[1][w] = __byte_perm(lo01, lo23, 0x7632);
-                        pl[2][w] = __byte_perm(hi01, hi23, 0x5410);
-                        pl[3][w] = __byte_perm(hi01, hi23, 0x7632);
+                    for (int i = 0; i < 4; ++i) {
+                        overflow |= fabsf(f[i]) > 1073741824.f;
+                        // balanced base-256 digits = bytes of (x + 0x00808080) ^ 0x00808080
+                        z[i] = ((uint32_t)__float2int_rn(f[i]) + 0x00808080u) ^ 0x00808080u;
                     }
-                    // K-major SWIZZLE_128B: one 128-byte row (128 consecutive matrix rows) per column
-                    const uint32_t off = (uint32_t)c * 128 + (uint32_t)((q ^ (c & 7)) << 4);
-#pragma unroll
-                    for (int d = 0; d < 4; ++d)
-                        *reinterpret_cast<uint4*>(buf + d * DIGIT_PLANE_BYTES + off) =
-                            make_uint4(pl[d][0], pl[d][1], pl[d][2], pl[d][3]);
+                    const uint32_t lo01 = __byte_perm(z[0], z[1], 0x5140), lo23 = __byte_perm(z[2], z[3], 0x5140);
+                    const uint32_t hi01 = __byte_perm(z[0], z[1], 0x7362), hi23 = __byte_perm(z[2], z[3], 0x7362);
+                    pl[0][w] = __byte_perm(lo01, lo23, 0x5410);
+                    pl[1][w] = __byte_perm(lo01, lo23, 0x7632);
+                    pl[2][w] = __byte_perm(hi01, hi23, 0x5410);
+                    pl[3][w] = __byte_perm(hi01, hi23, 0x7632);
                 }
+                // K-major SWIZZLE_128B: one 128-byte row (128 consecutive matrix rows) per column
+                const uint32_t off = (uint32_t)c * 128 + (uint32_t)((q ^ (c & 7)) << 4);
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                    *reinterpret_cast<uint4*>(buf + d * DIGIT_PLANE_BYTES + off) =
+                        make_uint4(pl[d][0], pl[d][1], pl[d][2], pl[d][3]);
             }
             fence_proxy_async_smem();
             mbar_arrive(a_full(b));
+        };
+        {
+            float4 v0[4][4], v1[4][4];
+            int n = 0, tile = blockIdx.x;
+            if (tile < tiles) issue(tile, v0);
+            while (tile < tiles) {
+                step(tile, n, v0, v1);
+                tile += gridDim.x; ++n;
+                if (tile >= tiles) break;
+                step(tile, n, v1, v0);
+                tile += gridDim.x; ++n;
+            }
         }
         if (overflow) atomicOr(info, 2);        // (Inf / NaN in the panel)
 
