@@ -1,8 +1,9 @@
 // Tensor-core apply for TALL panels: Q = A R^-1 as one split-precision tcgen05 product per
 // 128-row tile, so that the step runs at HBM speed instead of fp32-FMA issue speed.
 //
-//   trinv128_kernel     T = R^-1 (128 x 128 upper triangular) by back substitution in fp64, one CTA,
-//                       four threads per column of T.  Emits what the product needs: the column
+//   trinv128_kernel     T = R^-1 (128 x 128 upper triangular) in fp64 on one CTA: 8 x 8 diagonal blocks by
+//                       back substitution in registers, the other blocks by block distance on the
+//                       fp64 tensor path (mma.sync.m8n8k4.f64).  Emits what the product needs: the column
 //                       scales s_k (powers of two bringing ||a_k|| into [2^13, 2^14), so that every
 //                       entry of A s fits fp16), the matrix T~ = diag(1/s) T scaled by a power of two
 //                       and split into three fp16 planes, and the scalar that undoes that scale.
@@ -84,8 +85,7 @@ trinv128_kernel(const float* __restrict__ R, long ldr, TcApplyFactors* __restric
     extern __shared__ __align__(16) uint8_t smem_raw[];
     double* Ts = reinterpret_cast<double*>(smem_raw);                    // T(k, j) at k * TS_LD + j
     double* Rp = Ts + PW * TS_LD;                                        // R(i, k), i <= k, at k (k+1)/2 + i
-    double* rinv = Rp + R_PACKED;                                        // 1 / R(i, i)
-    float* sc = reinterpret_cast<float*>(rinv + PW);                     // column scales s_k
+    float* sc = reinterpret_cast<float*>(Rp + R_PACKED);                 // column scales s_k
     float* red = sc + PW;                                                // block max reduction
     double* Sscr = reinterpret_cast<double*>(red + 32);                  // 16 warps x 64 doubles
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -681,8 +681,6 @@ gram128_i8_kernel(const float* __restrict__ A, long lda, int m, const float* __r
 }
 
 }  // namespace
-
-size_t tc_apply_scratch_bytes() { return sizeof(TcApplyFactors); }
 
 int panel_gram_i8_grid(int m, int num_sms) {
     const int tiles = (m + PW - 1) / PW;
