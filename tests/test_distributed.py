@@ -77,3 +77,15 @@ def test_stack_layout():
     assert S.shape == (P * n, n) and S.stride() == (1, P * n)
     for p in range(P):
         assert torch.equal(S[p * n:(p + 1) * n, :], Rs[p])
+
+
+def test_host_A_requires_builtin_local_qr():
+    """`host_A` streams the row block through later_b200_rgsqrf_stream_in; it cannot be combined with
+    an injected local_qr (the CPU stand-ins of these tests)."""
+    import pytest, torch
+    from later_b200.tsqr import tsqr_rgsqrf
+    A = torch.zeros(256, 128).t().contiguous().t()
+    R = torch.zeros(128, 128)
+    with pytest.raises(ValueError, match="host_A needs the built-in"):
+        tsqr_rgsqrf(256, 128, A, 256, R, 128, local_qr=lambda *a: None, stack_qr=lambda *a: None,
+                    apply_w=lambda *a: None, host_A=A)
