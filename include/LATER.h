@@ -55,6 +55,33 @@ void generateNormalMatrix(float* dA, int m, int n);
 float snorm(int m, int n, float* dA);                // Frobenius norm of m*n contiguous floats
 void print_env();
 
+// Writes the m x n block of a device matrix as CSV (one row per line), as the reference's panel
+// drivers expect (reference include/LATER.h:168-196).
+template <typename T>
+void printMatrixDeviceBlock(const char* filename, int m, int n, T* dA, int lda) {
+    FILE* f = fopen(filename, "w");
+    if (!f) { printf("cannot open %s\n", filename); return; }
+    T* h = (T*)malloc(sizeof(T) * (size_t)lda * n);
+    cudaMemcpy(h, dA, sizeof(T) * ((size_t)lda * (n - 1) + m), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) fprintf(f, j + 1 == n ? "%lf\n" : "%lf,", (double)h[i + (size_t)j * lda]);
+    free(h);
+    fclose(f);
+}
+
+#define gpuErrchk(ans) { gpuAssert((ans), __FILE__, __LINE__); }
+inline void gpuAssert(cudaError_t code, const char* file, int line, bool abort = true) {
+    if (code != cudaSuccess) {
+        fprintf(stderr, "GPUassert: %s %s %d\n", cudaGetErrorString(code), file, line);
+        if (abort) exit(code);
+    }
+}
+#ifdef DEBUG_CUDA_KERNEL_LAUNCH
+#define CHECK_KERNEL() do { gpuErrchk(cudaDeviceSynchronize()); gpuErrchk(cudaPeekAtLastError()); } while (0)
+#else
+#define CHECK_KERNEL(x) do {} while (0)
+#endif
+
 __global__ void s2h(int m, int n, float* as, int ldas, __half* ah, int ldah);
 __global__ void h2s(int m, int n, __half* ah, int ldah, float* as, int ldas);
 __global__ void setEye(int m, int n, float* a, int lda);

@@ -27,7 +27,9 @@ enum {
     LATER_B200_EINVAL = -1,   /* bad shape / pointer / leading dimension */
     LATER_B200_ENOMEM = -2,   /* workspace could not be obtained */
     LATER_B200_ESTATE = -3,   /* call sequence error (e.g. tsqr_apply without a factorisation) */
-    LATER_B200_ENODEV = -4    /* no sm_100 device */
+    LATER_B200_ENODEV = -4,   /* no sm_100 device */
+    LATER_B200_ERANK = -5     /* the factorisation ran, but a panel was numerically rank deficient (or
+                                 the input held non-finite values): see later_b200_last_info */
 };
 
 /* Creates a context on `device`.  `stream` is a cudaStream_t (may be NULL = legacy default stream,
@@ -73,6 +75,10 @@ int later_b200_rgsqrf_stream_in(later_b200_ctx* ctx, int m, int n, const float* 
  * n must be 128.  Qh (optional, device fp16, leading dimension ldqh) receives the fp16 copy. */
 int later_b200_panel_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr);
 
+/* 32-column strip (reference mgs_caqr_panel_256x32, QR/panel.cu:65-134): A (m x 32) <- Q,
+ * R (32 x 32, or min(m, 32) square when m < 32) <- upper triangular factor.  n must be 32. */
+int later_b200_panel32_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr);
+
 /* TSQR back-multiplication for the row-sharded multi-GPU factorisation: Q <- Qh * W, where Qh is
  * the fp16 shadow of the Q most recently produced by later_b200_rgsqrf on this context (same m, n,
  * Q pointer) and W (device, n x n fp32) is this rank's block of the stacked-R factor's Q. */
@@ -101,6 +107,23 @@ int later_b200_gemm_update(later_b200_ctx* ctx, const void* Qh, int q_rows, int 
 
 /* Number of kernels launched by the most recent call on this context (for bench.py). */
 long later_b200_last_launch_count(const later_b200_ctx* ctx);
+
+/* Numerical status of the most recent factorisation on this context (later_b200_rgsqrf,
+ * _rgsqrf_host, _rgsqrf_stream_in, _panel_qr).  Waits for the context's stream, then fills
+ *   info[0]  1 + index of the first column whose Cholesky pivot was not positive (the panel is
+ *            numerically rank deficient: the pivot was clamped, Q and R are unreliable from there), 0 = none
+ *   info[1]  bit 0: non-finite / out-of-range input met by the integer Gram kernel;
+ *            bit 1: at least one tall panel was factored again from the fp64 Gram matrix
+ *   info[2]  number of such panels
+ *   info[3]  max over panels of ceil(-log2(min_k pivot_k / G_kk)), about 2 log2(cond(panel))
+ * and returns LATER_B200_ERANK if info[0] != 0 or bit 0 of info[1] is set, else 0.  The reference's
+ * MGS panel has no such report: it divides by the vanishing norm and carries on
+ * (reference QR/panel.cu:286-290).  later_b200_rgsqrf_host, which blocks anyway, returns
+ * LATER_B200_ERANK itself. */
+int later_b200_last_info(later_b200_ctx* ctx, int* info);
+
+/* Graph cache counters: factorisations replayed from a cached graph / graphs captured so far. */
+int later_b200_graph_stats(const later_b200_ctx* ctx, long* replays, long* captures);
 
 #ifdef __cplusplus
 }

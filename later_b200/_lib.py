@@ -24,6 +24,7 @@ SYMBOLS = {
     "later_b200_rgsqrf_stream_in": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                               C.c_void_p, C.c_int]),
     "later_b200_panel_qr": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "later_b200_panel32_qr": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "later_b200_tsqr_apply": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "later_b200_ormqr": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "later_b200_ormqr2": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -33,6 +34,8 @@ SYMBOLS = {
                                          C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long, C.c_void_p,
                                          C.c_long, C.c_int]),
     "later_b200_last_launch_count": (C.c_long, [_c_ctx]),
+    "later_b200_last_info": (C.c_int, [_c_ctx, C.POINTER(C.c_int)]),
+    "later_b200_graph_stats": (C.c_int, [_c_ctx, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
 }
 
 

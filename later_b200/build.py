@@ -19,19 +19,20 @@ LIB = ROOT / "later_b200" / "liblater_b200.so"
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
-# compat.cu defines __global__ kernels (setEye, clearTri, s2h) that the reference's test driver
-# launches from its own translation unit -> relocatable device code for that file only.
+# compat.cu and panel32.cu define __global__ kernels (setEye, clearTri, s2h; mgs_kernel, mgs_kernel2)
+# that the reference's test drivers launch from their own translation units -> relocatable device
+# code for those files only.
 SOURCES = {
     "tc_gemm.cu": [],
     "tc_update.cu": [],
     "tc_gram_cast.cu": [],
     "panel.cu": [],
     "panel_tc.cu": [],
+    "panel32.cu": ["-rdc=true"],
     "rgsqrf.cu": [],
     "ormqr.cu": [],
     "compat.cu": ["-rdc=true"],
 }
-HEADERS = ["ptx.cuh", "tc_gemm.cuh", "panel.cuh", "arena.h", "context.h"]
 
 
 def nvcc() -> str:
@@ -43,8 +44,10 @@ def nvcc() -> str:
 
 def _digest(extra: list[str]) -> str:
     h = hashlib.sha256()
-    for name in sorted(list(SOURCES) + HEADERS):
-        h.update((CSRC / name).read_bytes())
+    for src in sorted(CSRC.iterdir()):          # every source and header, whatever includes what
+        if src.suffix in (".cu", ".cuh", ".h"):
+            h.update(src.name.encode())
+            h.update(src.read_bytes())
     for inc in sorted((ROOT / "include").glob("*.h")):
         h.update(inc.read_bytes())
     h.update(" ".join(COMMON + extra).encode())

@@ -27,6 +27,10 @@ later_b200_ctx* default_ctx() {
 }
 
 void die_on(int rc, const char* what) {
+    if (rc == LATER_B200_ERANK) {   // the factorisation ran; the reference would carry on silently
+        fprintf(stderr, "later_b200: %s: %s\n", what, later_b200_last_error(default_ctx()));
+        return;
+    }
     if (rc != 0) {
         fprintf(stderr, "later_b200: %s failed (rc=%d): %s\n", what, rc,
                 later_b200_last_error(default_ctx()));
@@ -64,6 +68,21 @@ void later_rgsqrf(cudaCtxt, int m, int n, float* A, int lda, float* R, int ldr, 
 void mgs_caqr_panel_256x128(cudaCtxt, int m, int n, float* A, int lda, float* R, int ldr, float*) {
     die_on(later_b200_panel_qr(default_ctx(), m, n, A, lda, R, ldr), "mgs_caqr_panel_256x128");
 }
+
+void mgs_caqr_panel_256x32(cudaCtxt, int m, int n, float* A, int lda, float* R, int ldr, float*) {
+    if (n != 32) {   // the reference's message and behaviour (QR/panel.cu:67-71)
+        printf("[Error]: CAQR_32 does not support n!=32\n");
+        return;
+    }
+    die_on(later_b200_panel32_qr(default_ctx(), m, n, A, lda, R, ldr), "mgs_caqr_panel_256x32");
+}
+
+template <int M, int N>
+void hou_caqr_panel(cudaCtxt, int, int, float*, int, float*, int, float*) {
+    fprintf(stderr, "hou_caqr_panel<%d,%d>: Householder CAQR is out of scope of later_b200 (RGSQRF path only); "
+                    "A and R are left untouched\n", M, N);
+}
+template void hou_caqr_panel<256, 32>(cudaCtxt, int, int, float*, int, float*, int, float*);
 
 void later_ormqr(int m, int n, float* W, int ldw, float* Y, int ldy, float*) {
     die_on(later_b200_ormqr(default_ctx(), m, n, W, ldw, Y, ldy), "later_ormqr");

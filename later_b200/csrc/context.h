@@ -8,6 +8,19 @@
 #include <vector>
 
 #include "arena.h"
+#include "panel.cuh"
+
+namespace lb {
+// Diagnostic knobs, read from the environment once per context (later_b200_create).
+struct Options {
+    PanelOpts panel;
+    bool gram_cast = true;        // LB_GRAM_CAST = 0: always cast first, never in the Gram load path
+    int update_variant = 0;       // LB_UPDATE_VARIANT (later_b200_gemm_update only)
+    int ormqr_kchunk = 2048;      // LB_ORMQR_KCHUNK
+    bool gram_2cta = true;        // LB_GRAM_2CTA = 0: never use the CTA-pair Gram kernel
+};
+constexpr int kGraphSlots = 4;    // cached executable graphs per entry point (LRU)
+}  // namespace lb
 
 struct later_b200_ctx {
     int device = 0;
@@ -16,7 +29,12 @@ struct later_b200_ctx {
     bool use_graph = true;
     std::string error;
     lb::Arena arena;
+    lb::Options opts;
     long launches = 0;          // kernels launched by the most recent call
+    // status words of the most recent factorisation (lb::PanelInfo): device copy the kernels write,
+    // page-locked host copy filled by a D2H copy at the end of every factorisation
+    int* d_info = nullptr;
+    int* h_info = nullptr;
 
     // Layout of the most recent factorisation's workspace (for tsqr_apply and graph reuse).
     struct Plan {
@@ -37,13 +55,19 @@ struct later_b200_ctx {
     } plan;
 
     // Cached executable graphs: [0] factorisation of a device matrix, [1] the host entry point
-    // (same launches with the PCIe copies woven in as memcpy nodes on forked branches).
+    // (same launches with the PCIe copies woven in as memcpy nodes on forked branches).  Each entry
+    // point keeps the lb::kGraphSlots most recently used plans (shape + every pointer), so a caller
+    // that alternates between a few buffers or shapes (double-buffered out-of-core drivers,
+    // reference QR/later_oc_qr.cu:21; the QDWH iteration, EVD/later_qdwh_polar.cu:79) keeps replaying.
     struct GraphSlot {
         cudaGraphExec_t exec = nullptr;
         Plan plan;
         long launches = 0;
         bool seen = false;      // plan was launched directly once; capture on the next identical call
-    } graphs[2];
+        unsigned long tick = 0; // last use (LRU)
+    } graphs[2][lb::kGraphSlots];
+    unsigned long graph_tick = 0;
+    long graph_replays = 0, graph_captures = 0;   // counters (tests)
 
     // pipelined host path: copy streams and a pool of fork/join events
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -57,4 +81,21 @@ struct later_b200_ctx {
 namespace lb {
 int fail(later_b200_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(later_b200_ctx* ctx, cudaError_t e, const char* where);
+
+// Makes the context's device current for the duration of a C-ABI call and restores the caller's.
+class DeviceGuard {
+public:
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+        err_ = prev_ == device ? cudaSuccess : cudaSetDevice(device);
+        if (prev_ == device) prev_ = -1;          // nothing to restore
+    }
+    ~DeviceGuard() { if (prev_ >= 0) cudaSetDevice(prev_); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+    cudaError_t error() const { return err_; }
+private:
+    int prev_ = -1;
+    cudaError_t err_ = cudaSuccess;
+};
 }  // namespace lb

@@ -158,7 +158,8 @@ int ormqr_impl(later_b200_ctx* ctx, int m, int n, float* W, int ldw, const float
         return fail(ctx, LATER_B200_EINVAL, "later_ormqr needs n to be a multiple of 256");
     if (m < n || m % 8 != 0) return fail(ctx, LATER_B200_EINVAL, "m must be >= n and a multiple of 8");
     if (ldw < m || ldy < m) return fail(ctx, LATER_B200_EINVAL, "leading dimension too small");
-    cudaError_t e = cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = guard.error();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
 
     const long ldp = round_up(m, 8);
@@ -187,7 +188,7 @@ int ormqr_impl(later_b200_ctx* ctx, int m, int n, float* W, int ldw, const float
 
     Ormqr o{};
     o.ctx = ctx; o.st = ctx->stream;
-    if (const char* v = getenv("LB_ORMQR_KCHUNK")) o.kChunk = std::max(BK, atoi(v) / BK * BK);
+    o.kChunk = ctx->opts.ormqr_kchunk;
     o.slot = reinterpret_cast<unsigned*>(scal + 32);
     o.sW = scal; o.sY = scal + 2; o.sK = scal + 4; o.unscale = scal + 6;
     o.check(cudaMemsetAsync(scal, 0, 64 * sizeof(float), o.st));

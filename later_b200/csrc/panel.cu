@@ -73,7 +73,8 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
 }
 
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
-gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restrict__ part) {
+gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restrict__ part,
+                   const int* __restrict__ cond) {
     __shared__ __align__(16) double As[GRAM_ROWS][GRAM_LDS];   // 16.5 KiB
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -121,6 +122,7 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
 
     pdl_trigger();
     pdl_wait();      // the panel is written by the preceding update kernel
+    if (cond && *cond == 0) return;   // fallback launch of a panel that did not need it (whole grid)
     int chunk = blockIdx.x;
     if (chunk < nchunks) prefetch(chunk);
     for (; chunk < nchunks; chunk += gridDim.x) {
@@ -180,12 +182,13 @@ gram128_f64_kernel(const float* __restrict__ A, long lda, int m, double* __restr
 // Also clears the block-row flags of the factor hand-over for this panel.
 __global__ void __launch_bounds__(1024)
 gram128_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ G,
-                      int* __restrict__ flags) {
+                      int* __restrict__ flags, const int* __restrict__ cond) {
     __shared__ double sh[32][33];
     const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int idx = blockIdx.x * 32 + e;
     pdl_trigger();
     pdl_wait();
+    if (cond && *cond == 0) return;
     if (blockIdx.x == 0 && threadIdx.x < 4) flags[threadIdx.x] = 0;
     double s = 0.0;
     if (idx < GRAM_ELEMS)
@@ -230,8 +233,10 @@ constexpr int CHOL_RING = 8;            // ring slots (column pairs in flight)
 struct CholShared {
     double col[CHOL_RING][2][PW];
     double rs[PW];              // 1 / L(c, c), written by the owner before it publishes column c
+    double gdiag[PW];           // G(c, c), for the pivot-ratio check of the output warps
     uint64_t empty[CHOL_RING];  // mbarriers: all readers of a slot are done
     int published;              // number of column pairs published so far (release / acquire)
+    int bad;                    // 1 + local column of the first non-positive pivot (0 = none)
 #ifdef LB_CHOL_TRACE
     long long tr[64][8];        // per pair: owner timestamps
 #endif
@@ -240,7 +245,11 @@ struct CholShared {
 struct CholOut {
     float* R; long ldr;
     PanelFactors* fac;
-    int* info;
+    int* info;          // status words of the factorisation (PanelInfo)
+    int col0;           // global index of the panel's first column
+    int check_redo;     // 1: this is the first attempt of an integer-Gram panel - a small or bad pivot
+                        //    raises info[INFO_REDO] instead of being reported
+    double tau;         // pivot-ratio threshold of that check
 };
 
 __device__ __forceinline__ void chol_publish(int* counter, int value) {
@@ -295,7 +304,7 @@ __device__ __forceinline__ void chol_emit_pair(double (&a)[8][8], int c, int ty,
     if (lane == 0) { sh.rs[c] = rs0; sh.rs[c + 1] = rs1; }
     __syncwarp();
     if (lane == 0) chol_publish(&sh.published, (c >> 1) + 1);
-    if (lane == 0 && (bad0 || bad1)) atomicExch(o.info, c + (bad0 ? 1 : 2));   // off the chain
+    if (lane == 0 && (bad0 || bad1)) atomicCAS(&sh.bad, 0, c + (bad0 ? 1 : 2));   // off the chain
 }
 
 template <int CB>
@@ -363,6 +372,7 @@ __device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, i
 __device__ __forceinline__ void chol_output_warp(int j, int lane, CholShared& sh, const CholOut& o) {
     const int pl = perm32(lane);
     const int i = lane + 32 * j;
+    double min_ratio = 1.0;                // lanes 0, 1 of output warp 0: min piv_k / G_kk so far
 #pragma unroll 1
     for (int s = 0; s < PW / 2; ++s) {
         const int slot = s & (CHOL_RING - 1);
@@ -377,7 +387,14 @@ __device__ __forceinline__ void chol_output_warp(int j, int lane, CholShared& sh
                 else o.fac->Roff[off_index(rb, j)][rr][pl] = l;
             }
         }
-        if (j == 0 && lane < 2) o.fac->rinv[2 * s + lane] = (float)sh.rs[2 * s + lane];
+        if (j == 0 && lane < 2) {
+            const double rs = sh.rs[2 * s + lane];
+            o.fac->rinv[2 * s + lane] = (float)rs;
+            const double gd = sh.gdiag[2 * s + lane];
+            // piv / G_kk = 1 / (rs^2 G_kk); a zero or non-finite G_kk counts as breakdown
+            const double ratio = (gd > 0.0 && gd < 1e300) ? 1.0 / (rs * rs * gd) : 0.0;
+            min_ratio = fmin(min_ratio, ratio);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sh.empty[slot]));
         if ((s & 15) == 15) {                  // columns 32 b .. 32 b + 31 are out: publish block-row b
@@ -386,22 +403,48 @@ __device__ __forceinline__ void chol_output_warp(int j, int lane, CholShared& sh
             if (j == 0 && lane == 0) *reinterpret_cast<volatile int*>(&o.fac->flag[s >> 4]) = 1;
         }
     }
+    // Status of the panel (every column has been published, so sh.bad is final).
+    if (j == 0) {
+        const double other = __shfl_sync(0xffffffffu, min_ratio, 1);
+        if (lane == 0) {
+            min_ratio = fmin(min_ratio, other);
+            const int bad = *reinterpret_cast<volatile int*>(&sh.bad);
+            if (o.check_redo) {
+                o.info[INFO_REDO] = (bad != 0 || !(min_ratio >= o.tau)) ? 1 : 0;
+            } else {
+                if (bad != 0) atomicCAS(&o.info[INFO_BAD_COLUMN], 0, o.col0 + bad);
+                int e = 0;
+                if (min_ratio > 0.0) { frexp(min_ratio, &e); e = 1 - e; } else { e = 2047; }
+                atomicMax(&o.info[INFO_COND_LOG2], e);      // ~ -log2(min ratio), rounded up
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
 chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
-               PanelFactors* __restrict__ fac, int* __restrict__ info) {
+               PanelFactors* __restrict__ fac, int* __restrict__ info, int col0, int check_redo,
+               double tau, const int* __restrict__ cond) {
     __shared__ CholShared sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = 2 * warp + (lane >> 4);      // column residue (compute warps)
     const int ty = lane & 15;                   // row residue
-    const CholOut o{R, ldr, fac, info};
+    const CholOut o{R, ldr, fac, info, col0, check_redo, tau};
     if (threadIdx.x == 0) {
         for (int s = 0; s < CHOL_RING; ++s) mbar_init(smem_u32(&sh.empty[s]), 8 + CHOL_OUT_WARPS);
         sh.published = 0;
+        sh.bad = 0;
         fence_barrier_init();
     }
     pdl_wait();      // G and the cleared flags come from the reduce kernel
+    if (cond) {      // fallback launch: runs only if the first attempt asked for it
+        if (*cond == 0) return;
+        if (threadIdx.x == 0) { atomicAdd(&info[INFO_FALLBACKS], 1); atomicOr(&info[INFO_FLAGS], 2); }
+    }
+    if (warp >= 8) {
+        const int k = threadIdx.x - 256;
+        sh.gdiag[k] = gram_elem(G, k, k);
+    }
     // Only now may the dependent apply grid start: it synchronises on fac->flag[] (not on the
     // completion of this grid), so the flags must already have been cleared by the reduce kernel.
     pdl_trigger();
@@ -643,75 +686,70 @@ cudaError_t panel_init() {
     return e != cudaSuccess ? e : tc_apply_init();
 }
 
-// LB_APPLY_TC = 0 / 1 forces the forward-substitution / tensor-core apply (tests, profiling).
-static int apply_tc_override() {
-    const char* s = getenv("LB_APPLY_TC");
-    return s ? atoi(s) : -1;
-}
-
-// LB_GRAM_I8 = 0 keeps the fp64 (DMMA) Gram kernel everywhere.
-bool panel_uses_i8_gram(int m, int num_sms, const float* A, long lda, bool allow_tc) {
-    const char* s = getenv("LB_GRAM_I8");
-    if (s && atoi(s) == 0) return false;
+bool panel_uses_i8_gram(int m, int num_sms, const float* A, long lda, bool allow_tc, const PanelOpts& opts) {
+    if (!opts.gram_i8) return false;
     const bool aligned = lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
-    int min_rows = kI8GramMinRows;
-    if (const char* t = getenv("LB_GRAM_I8_MIN_ROWS")) min_rows = atoi(t);
-    return allow_tc && aligned && m >= min_rows && panel_gram_i8_fits(m, num_sms);
+    return allow_tc && aligned && m >= opts.gram_i8_min_rows && panel_gram_i8_fits(m, num_sms);
 }
 
-bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc) {
-    const int ov = apply_tc_override();
+bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc, const PanelOpts& opts) {
+    const int ov = opts.apply_tc;
     const bool tc_ok = lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
     return tc_ok && (ov == 1 || (ov != 0 && allow_tc && m >= kTcApplyMinRows));
 }
 
-int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_tc) {
-    return 4 + (panel_uses_tc_apply(m, A, lda, allow_tc) ? 1 : 0) +
-           (panel_uses_i8_gram(m, num_sms, A, lda, allow_tc) ? 1 : 0);
+int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_tc, const PanelOpts& opts) {
+    return 4 + (panel_uses_tc_apply(m, A, lda, allow_tc, opts) ? 1 : 0) +
+           (panel_uses_i8_gram(m, num_sms, A, lda, allow_tc, opts) ? 4 : 0);
 }
 
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
-                        long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc, bool colmax_ready) {
+                        long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc,
+                        const PanelOpts& opts, int* info, int col0, bool colmax_ready) {
     const ScratchLayout L = scratch_layout(m, num_sms);
     uint8_t* base = static_cast<uint8_t*>(scratch);
     double* part = reinterpret_cast<double*>(base + L.part_off);
     double* G = reinterpret_cast<double*>(base + L.g_off);
     PanelFactors* fac = reinterpret_cast<PanelFactors*>(base + L.fac_off);
-    int* info = reinterpret_cast<int*>(base + L.info_off);
-    int ggrid = gram_grid(m, num_sms);
+    const int ggrid = gram_grid(m, num_sms);
+    const int rgrid = (GRAM_ELEMS + 31) / 32;
+    const int* never = nullptr;
 
     cudaError_t le;
-    if (panel_uses_i8_gram(m, num_sms, A, lda, allow_tc)) {
-        ggrid = panel_gram_i8_grid(m, num_sms);
+    if (panel_uses_i8_gram(m, num_sms, A, lda, allow_tc, opts)) {
+        // first attempt from the integer Gram matrix; the Cholesky kernel decides whether it is good
+        // enough (info[INFO_REDO]), and the fp64 chain below runs for real only if it is not
+        const int igrid = panel_gram_i8_grid(m, num_sms);
         if ((le = panel_gram_i8(stream, num_sms, m, A, lda, reinterpret_cast<float*>(base + L.colmax_off),
-                                colmax_ready, part, info + 1)) != cudaSuccess)
+                                colmax_ready, part, info + INFO_FLAGS)) != cudaSuccess)
             return le;
-    } else if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream,
-                                (const float*)A, lda, m, part)) != cudaSuccess) {
-        return le;
+        if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
+                             igrid, G, fac->flag, never)) != cudaSuccess) return le;
+        if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr,
+                             fac, info, col0, 1, opts.i8_fallback_tau, never)) != cudaSuccess) return le;
+        const int* redo = info + INFO_REDO;
+        if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream, (const float*)A,
+                             lda, m, part, redo)) != cudaSuccess) return le;
+        if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
+                             ggrid, G, fac->flag, redo)) != cudaSuccess) return le;
+        if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr,
+                             fac, info, col0, 0, 0.0, redo)) != cudaSuccess) return le;
+    } else {
+        if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream, (const float*)A,
+                             lda, m, part, never)) != cudaSuccess) return le;
+        if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
+                             ggrid, G, fac->flag, never)) != cudaSuccess) return le;
+        if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr,
+                             fac, info, col0, 0, 0.0, never)) != cudaSuccess) return le;
     }
-    if ((le = launch_pdl(gram128_reduce_kernel, dim3((GRAM_ELEMS + 31) / 32), dim3(1024), 0, stream,
-                         (const double*)part, ggrid, G, fac->flag)) != cudaSuccess) return le;
-    if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr, fac,
-                         info)) != cudaSuccess) return le;
-    if (panel_uses_tc_apply(m, A, lda, allow_tc))
+    if (panel_uses_tc_apply(m, A, lda, allow_tc, opts))
         return panel_apply_tc(stream, num_sms, m, A, lda, R, ldr, Qh, ldqh,
                               reinterpret_cast<TcApplyFactors*>(base + L.tc_off));
     // programmatic dependent launch: the apply grid may start while the Cholesky grid is running
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((m + APPLY_ROWS - 1) / APPLY_ROWS);
-    cfg.blockDim = dim3(APPLY_THREADS);
-    cfg.dynamicSmemBytes = sizeof(ApplySmem);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
     const PanelFactors* cfac = fac;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, apply128_kernel, A, lda, m, cfac, Qh, ldqh);
-    if (e != cudaSuccess) return e;
-    return cudaGetLastError();
+    le = launch_pdl(apply128_kernel, dim3((m + APPLY_ROWS - 1) / APPLY_ROWS), dim3(APPLY_THREADS),
+                    sizeof(ApplySmem), stream, A, lda, m, cfac, Qh, ldqh);
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace lb

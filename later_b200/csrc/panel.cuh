@@ -18,6 +18,36 @@ namespace lb {
 
 constexpr int kPanelWidth = 128;
 
+// ---- tensor-core kernels for tall panels (panel_tc.cu)
+// Rows from which panel_qr128 switches from the fp32 forward-substitution apply (hidden behind the
+// Cholesky kernel on short panels) to the split-precision tcgen05 apply (HBM-bound).
+constexpr int kTcApplyMinRows = 65536;
+// Rows from which the Gram matrix is formed on the integer tensor path instead of DMMA.
+constexpr int kI8GramMinRows = 65536;
+
+// Knobs of the panel path; read from the environment ONCE, when a context is created (tests and
+// profiling only - the defaults are the product).
+struct PanelOpts {
+    int apply_tc = -1;                       // LB_APPLY_TC: -1 auto, 0 forward substitution, 1 tensor-core apply
+    bool gram_i8 = true;                     // LB_GRAM_I8 = 0 keeps the fp64 (DMMA) Gram kernel everywhere
+    int gram_i8_min_rows = kI8GramMinRows;   // LB_GRAM_I8_MIN_ROWS
+    // LB_I8_FALLBACK_TAU: an integer-Gram panel whose smallest Cholesky pivot ratio piv_k / G_kk falls
+    // below this is factored again from the fp64 Gram matrix (see panel_qr128)
+    double i8_fallback_tau = 0.0078125;
+};
+
+// Status words of a factorisation (device int[kInfoWords], cleared by the caller before the first
+// panel, read back after the last one; include/later_b200.h: later_b200_last_info).
+constexpr int kInfoWords = 8;
+enum PanelInfo : int {
+    INFO_BAD_COLUMN = 0,   // 1 + first (global) column whose Cholesky pivot was not positive, 0 = none
+    INFO_FLAGS = 1,        // bit 0: non-finite / out-of-range entry met by the integer Gram kernel
+                           // bit 1: at least one panel fell back from the integer to the fp64 Gram matrix
+    INFO_FALLBACKS = 2,    // number of such panels
+    INFO_COND_LOG2 = 3,    // max over panels of ceil(-log2(min_k piv_k / G_kk)): ~ 2 log2(cond(panel))
+    INFO_REDO = 4,         // scratch: "factor this panel again" flag between the two Cholesky launches
+};
+
 // Scratch (bytes) needed by panel_qr128 for an m-row panel on a device with num_sms SMs.
 size_t panel_scratch_bytes(int m, int num_sms);
 
@@ -28,23 +58,28 @@ size_t panel_scratch_bytes(int m, int num_sms);
 // Q rounded to fp16 anyway, says yes; the stand-alone panel entry point, which replaces the
 // reference's all-fp32 panel, says no.
 // colmax_ready: panel_colmax_scratch() already holds this panel's column maxima.
+// info: the factorisation's status words (see PanelInfo); col0: global index of the panel's first
+// column (for INFO_BAD_COLUMN).
+//
+// Breakdown handling.  CholeskyQR needs G accurate relative to its smallest eigenvalue.  The fp64
+// Gram matrix (exact products, fp64 sums) is good for cond(panel) up to ~1e6-1e7; the integer Gram
+// matrix drops digit pairs below 2^-26 of a product, a systematic error of ~1e-8 |G|, so
+// its panels are checked: if the smallest pivot ratio piv_k / G_kk (~ 1 / cond^2) is below
+// opts.i8_fallback_tau, or a pivot is not positive, the panel is factored AGAIN from the fp64 Gram
+// matrix.  The three fallback kernels are always enqueued (the launch sequence must not depend on
+// data: it is replayed from a CUDA graph) and exit at once unless the flag is set.  A non-positive
+// pivot on the fp64 path is clamped and reported in info[INFO_BAD_COLUMN].
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
                         long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc,
-                        bool colmax_ready = false);
+                        const PanelOpts& opts, int* info, int col0, bool colmax_ready = false);
 
 cudaError_t panel_init();
-// Which apply panel_qr128 will use (4 launches per panel with forward substitution, 5 with the
-// tensor-core apply: + the triangular inverse).
-bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc);
-bool panel_uses_i8_gram(int m, int num_sms, const float* A, long lda, bool allow_tc);
-int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_tc);
-
-// ---- tensor-core apply for tall panels (panel_tc.cu)
-// Rows from which panel_qr128 switches from the fp32 forward-substitution apply (hidden behind the
-// Cholesky kernel on short panels) to the split-precision tcgen05 apply (HBM-bound).
-constexpr int kTcApplyMinRows = 65536;
-// Rows from which the Gram matrix is formed on the integer tensor path instead of DMMA.
-constexpr int kI8GramMinRows = 65536;
+// Which kernels panel_qr128 will use (4 launches per panel with forward substitution, 5 with the
+// tensor-core apply: + the triangular inverse; + 4 or 5 with the integer Gram: column maxima unless
+// ready, the Gram kernel itself and the three conditional fallback kernels).
+bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc, const PanelOpts& opts);
+bool panel_uses_i8_gram(int m, int num_sms, const float* A, long lda, bool allow_tc, const PanelOpts& opts);
+int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_tc, const PanelOpts& opts);
 
 struct TcApplyFactors {
     // three fp16 planes t1 + t2 + t3 = fp32(diag(1/s) R^-1) * 2^e exactly, column-major

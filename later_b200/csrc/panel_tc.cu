@@ -587,7 +587,7 @@ gram128_i8_kernel(const float* __restrict__ A, long lda, int m, const float* __r
                     uint32_t z[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        overflow |= fabsf(f[i]) > 1073741824.f;
+                        overflow |= !(fabsf(f[i]) <= 1073741824.f);     // (also true for NaN)
                         // balanced base-256 digits = bytes of (x + 0x00808080) ^ 0x00808080
                         z[i] = ((uint32_t)__float2int_rn(f[i]) + 0x00808080u) ^ 0x00808080u;
                     }
@@ -620,7 +620,7 @@ gram128_i8_kernel(const float* __restrict__ A, long lda, int m, const float* __r
                 tile += gridDim.x; ++n;
             }
         }
-        if (overflow) atomicOr(info, 2);        // (Inf / NaN in the panel)
+        if (overflow) atomicOr(info, 1);        // INFO_FLAGS bit 0 (Inf / NaN in the panel)
 
         // ---- drain: G(j,k) 2^(E_j + E_k) = sum_g acc_g(j,k) 256^(g+3), upper 32 x 32 blocks only.
         // Groups 0 and 2 (s + t = 3, 5) hold one pair of each mirror couple: X = acc_0 256^3 + acc_2 256^5

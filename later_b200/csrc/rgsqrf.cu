@@ -215,9 +215,9 @@ struct Recursion {
             colmax_col = -1;
             check(panel_qr128(st, ctx->num_sms, p->m, p->A + (long)c0 * p->lda, p->lda,
                               p->R + c0 + (long)c0 * p->ldr, p->ldr, p->Qh + (long)c0 * p->ldh,
-                              p->ldh, p->panel_scratch, true, ready));
-            launches += panel_launch_count(p->m, ctx->num_sms, p->A + (long)c0 * p->lda, p->lda, true) -
-                        (ready ? 1 : 0);
+                              p->ldh, p->panel_scratch, true, ctx->opts.panel, ctx->d_info, c0, ready));
+            launches += panel_launch_count(p->m, ctx->num_sms, p->A + (long)c0 * p->lda, p->lda, true,
+                                           ctx->opts.panel) - (ready ? 1 : 0);
         } else {
             qr(c0, w / 2);
             node_tail(c0, w);
@@ -247,9 +247,7 @@ struct Recursion {
         float* R12 = p->R + c0 + (long)cb * p->ldr;
         // (the mirror block R21, which the algorithm never produces, is written as zero on the way)
         float* Z = zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr;
-        const char* fv = getenv("LB_GRAM_CAST");      // 0: always cast first (tests, profiling)
-        const bool fuse_ok = !fv || atoi(fv) != 0;
-        const bool fused = b_is_input && fuse_ok && splits >= 2 && tc_gram_cast_supports(h) &&
+        const bool fused = b_is_input && ctx->opts.gram_cast && splits >= 2 && tc_gram_cast_supports(h) &&
                            p->m >= kTcApplyMinRows && p->lda % 4 == 0 &&
                            (reinterpret_cast<uintptr_t>(p->A) & 15) == 0;
         if (fused) {
@@ -271,7 +269,8 @@ struct Recursion {
             // update leaves their maxima behind and saves that kernel its first pass over the panel
             // (worth its ~2 % of epilogue work only when that pass would come from HBM: a panel that
             // still sits in the 126 MB L2 after this update is scanned in ~10 us)
-            const bool want = panel_uses_i8_gram(p->m, ctx->num_sms, p->A + (long)cb * p->lda, p->lda, true) &&
+            const bool want = panel_uses_i8_gram(p->m, ctx->num_sms, p->A + (long)cb * p->lda, p->lda, true,
+                                                 ctx->opts.panel) &&
                               (size_t)p->m * kPanelWidth * sizeof(float) > ((size_t)96 << 20);
             check(tc_update_tma(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, nb, p->A, p->m,
                                 p->n, p->lda, cb, p->Qh, p->ldh, true,
@@ -333,6 +332,7 @@ int validate(later_b200_ctx* ctx, int m, int n, const void* A, int lda, const vo
     if (m % 8 != 0) return fail(ctx, LATER_B200_EINVAL, "m must be a multiple of 8");
     if (lda < m || ldr < n) return fail(ctx, LATER_B200_EINVAL, "leading dimension too small");
     if ((long)m * n > (long)1 << 34) return fail(ctx, LATER_B200_EINVAL, "matrix too large");
+    if (n > 65536) return fail(ctx, LATER_B200_EINVAL, "n must be <= 65536");   // (grid.y of the cast kernel)
     return 0;
 }
 
@@ -377,6 +377,8 @@ int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
         (e = make_tensor_map_f16(&rec.q256, qm, 64, 256)) != cudaSuccess ||
         (e = make_tensor_map_f16(&rec.q64, qm, 64, 64)) != cudaSuccess)
         return cuda_fail(ctx, e, "tensor map encode");
+    if ((e = cudaMemsetAsync(ctx->d_info, 0, kInfoWords * sizeof(int), ctx->stream)) != cudaSuccess)
+        return cuda_fail(ctx, e, "info clear");
     HostPipe pipe;
     if (stage == STAGE_HOST) {
         pipe.ctx = ctx;
@@ -394,6 +396,10 @@ int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
         if (pipe.err != cudaSuccess) return cuda_fail(ctx, pipe.err, "host pipeline");
     }
     if (rec.err != cudaSuccess) return cuda_fail(ctx, rec.err, "rgsqrf enqueue");
+    // the status words travel to page-locked host memory behind the last kernel (later_b200_last_info)
+    if ((e = cudaMemcpyAsync(ctx->h_info, ctx->d_info, kInfoWords * sizeof(int), cudaMemcpyDeviceToHost,
+                             ctx->stream)) != cudaSuccess)
+        return cuda_fail(ctx, e, "info read-back");
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "rgsqrf launch");
     *launches = rec.launches;
@@ -406,45 +412,46 @@ bool same_plan(const later_b200_ctx::Plan& a, const later_b200_ctx::Plan& b) {
            a.hA == b.hA && a.hlda == b.hlda && a.hR == b.hR && a.hldr == b.hldr;
 }
 
-// Runs one stage on ctx->stream: replays the cached graph of that stage when shapes and pointers
-// match, otherwise captures and instantiates it (or launches directly with graphs disabled).
+// Runs one stage on ctx->stream: replays the cached graph of that stage when a cached plan (shape
+// and every pointer) matches, otherwise launches directly (first sight of a plan) or captures and
+// instantiates it (second sight).  kGraphSlots plans are kept per stage, least recently used evicted.
 int run_stage(later_b200_ctx* ctx, int stage) {
     cudaError_t e;
-    if (!ctx->use_graph) {
+    auto direct = [&]() {
         long l = 0;
         int rc = enqueue_stage(ctx, stage, &l);
         ctx->launches = l;
         return rc;
-    }
-    auto& slot = ctx->graphs[stage];
-    // A plan seen for the first time is launched directly: capturing and instantiating a graph of
-    // ~900 nodes costs tens of milliseconds, which only pays off from the second identical call on
-    // (the reference's driver, test/test_qr.cu, calls the factorisation exactly once per process).
-    if (!slot.exec && !(slot.seen && same_plan(slot.plan, ctx->plan))) {
-        long l = 0;
-        int rc = enqueue_stage(ctx, stage, &l);
-        ctx->launches = l;
-        slot.plan = ctx->plan;
-        slot.seen = true;
-        return rc;
-    }
-    if (slot.exec && same_plan(slot.plan, ctx->plan)) {
-        e = cudaGraphLaunch(slot.exec, ctx->stream);
-        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
-        ctx->launches = slot.launches;
-        return 0;
-    }
-    if (slot.exec) {
-        cudaGraphExecDestroy(slot.exec);
-        slot.exec = nullptr;
-        if (!same_plan(slot.plan, ctx->plan)) {   // a different problem: start over with a direct launch
-            long l = 0;
-            int rc = enqueue_stage(ctx, stage, &l);
-            ctx->launches = l;
-            slot.plan = ctx->plan;
-            slot.seen = true;
-            return rc;
+    };
+    if (!ctx->use_graph) return direct();
+    later_b200_ctx::GraphSlot* slot = nullptr;
+    for (auto& g : ctx->graphs[stage])
+        if (g.seen && same_plan(g.plan, ctx->plan)) { slot = &g; break; }
+    if (!slot) {
+        // A plan seen for the first time is launched directly: capturing and instantiating a graph of
+        // ~900 nodes costs tens of milliseconds, which only pays off from the second identical call on
+        // (the reference's driver, test/test_qr.cu, calls the factorisation exactly once per process).
+        int rc = direct();
+        later_b200_ctx::GraphSlot* victim = &ctx->graphs[stage][0];
+        for (auto& g : ctx->graphs[stage]) {
+            if (!g.seen) { victim = &g; break; }
+            if (g.tick < victim->tick) victim = &g;
         }
+        if (victim->exec) cudaGraphExecDestroy(victim->exec);
+        victim->exec = nullptr;
+        victim->plan = ctx->plan;
+        victim->seen = rc == 0;
+        victim->launches = ctx->launches;
+        victim->tick = ++ctx->graph_tick;
+        return rc;
+    }
+    slot->tick = ++ctx->graph_tick;
+    if (slot->exec) {
+        e = cudaGraphLaunch(slot->exec, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
+        ctx->launches = slot->launches;
+        ++ctx->graph_replays;
+        return 0;
     }
     // Capture on a private stream so the legacy default stream can be the context's stream.
     cudaStream_t cap = nullptr;
@@ -466,13 +473,13 @@ int run_stage(later_b200_ctx* ctx, int stage) {
     cudaStreamDestroy(cap);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "end capture");
-    e = cudaGraphInstantiate(&slot.exec, graph, 0);
+    e = cudaGraphInstantiate(&slot->exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { slot.exec = nullptr; return cuda_fail(ctx, e, "graph instantiate"); }
-    slot.plan = ctx->plan;
-    slot.launches = launches;
+    if (e != cudaSuccess) { slot->exec = nullptr; return cuda_fail(ctx, e, "graph instantiate"); }
+    slot->launches = launches;
     ctx->launches = launches;
-    e = cudaGraphLaunch(slot.exec, ctx->stream);
+    ++ctx->graph_captures;
+    e = cudaGraphLaunch(slot->exec, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphLaunch");
     return 0;
 }
@@ -480,15 +487,38 @@ int run_stage(later_b200_ctx* ctx, int stage) {
 int rgsqrf_prepare(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
     int rc = validate(ctx, m, n, A, lda, R, ldr);
     if (rc) return rc;
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
     return prepare_plan(ctx, m, n, A, lda, R, ldr);
 }
 
 int rgsqrf_device(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
+    if (!ctx) return LATER_B200_EINVAL;
+    DeviceGuard guard(ctx->device);
+    if (guard.error() != cudaSuccess) return cuda_fail(ctx, guard.error(), "cudaSetDevice");
     int rc = rgsqrf_prepare(ctx, m, n, A, lda, R, ldr);
     if (rc) return rc;
     return run_stage(ctx, STAGE_ALL);
+}
+
+void read_options(Options& o) {
+    auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+    o.panel.apply_tc = geti("LB_APPLY_TC", -1);
+    o.panel.gram_i8 = geti("LB_GRAM_I8", 1) != 0;
+    o.panel.gram_i8_min_rows = geti("LB_GRAM_I8_MIN_ROWS", kI8GramMinRows);
+    if (const char* v = getenv("LB_I8_FALLBACK_TAU")) o.panel.i8_fallback_tau = atof(v);
+    o.gram_cast = geti("LB_GRAM_CAST", 1) != 0;
+    o.update_variant = geti("LB_UPDATE_VARIANT", 0);
+    o.ormqr_kchunk = std::max(64, geti("LB_ORMQR_KCHUNK", 2048) / 64 * 64);
+    o.gram_2cta = geti("LB_GRAM_2CTA", 1) != 0;
+}
+
+std::string rank_message(const int* info) {
+    char buf[200];
+    if (info[INFO_BAD_COLUMN])
+        snprintf(buf, sizeof buf, "numerically rank-deficient input: non-positive Cholesky pivot at column %d "
+                 "(clamped; Q and R are not reliable from that column on)", info[INFO_BAD_COLUMN] - 1);
+    else
+        snprintf(buf, sizeof buf, "non-finite or out-of-range entries in the input");
+    return buf;
 }
 
 __global__ void cast_matrix_kernel(const float* __restrict__ S, long lds, int rows, int cols,
@@ -519,25 +549,29 @@ int later_b200_create(later_b200_ctx** out, int device, void* stream) {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LATER_B200_ENODEV;
     if (prop.major != 10) return LATER_B200_ENODEV;  // tcgen05 kernels: sm_100a only, no fallback
-    if (cudaSetDevice(device) != cudaSuccess) return LATER_B200_ENODEV;
+    DeviceGuard guard(device);
+    if (guard.error() != cudaSuccess) return LATER_B200_ENODEV;
     later_b200_ctx* ctx = new (std::nothrow) later_b200_ctx();
     if (!ctx) return LATER_B200_ENOMEM;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     ctx->stream = static_cast<cudaStream_t>(stream);
     ctx->arena.bind(ctx->stream);
-    // keep freed workspace cached in the default pool instead of returning it to the OS
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long thresh = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    read_options(ctx->opts);
+    cudaError_t e = cudaMalloc(&ctx->d_info, kInfoWords * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_info, kInfoWords * sizeof(int));
+    if (e == cudaSuccess) {
+        memset(ctx->h_info, 0, kInfoWords * sizeof(int));
+        e = cudaMemset(ctx->d_info, 0, kInfoWords * sizeof(int));
     }
-    cudaError_t e = tc_gemm_init();
+    if (e == cudaSuccess) e = tc_gemm_init();
     if (e == cudaSuccess) e = tc_gram_cast_init();
     if (e == cudaSuccess) e = tc_update_init();
     if (e == cudaSuccess) e = panel_init();
     if (e != cudaSuccess) {
-        int rc = cuda_fail(ctx, e, "kernel attribute setup");
+        int rc = cuda_fail(ctx, e, "context setup");
+        if (ctx->d_info) cudaFree(ctx->d_info);
+        if (ctx->h_info) cudaFreeHost(ctx->h_info);
         delete ctx;
         return rc;
     }
@@ -547,16 +581,19 @@ int later_b200_create(later_b200_ctx** out, int device, void* stream) {
 
 int later_b200_destroy(later_b200_ctx* ctx) {
     if (!ctx) return LATER_B200_EINVAL;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& g : ctx->graphs)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& stage : ctx->graphs)
+        for (auto& g : stage)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     for (auto& ev : ctx->events)
         if (ev) cudaEventDestroy(ev);
     if (ctx->dA) cudaFree(ctx->dA);
     if (ctx->dR) cudaFree(ctx->dR);
+    if (ctx->d_info) cudaFree(ctx->d_info);
+    if (ctx->h_info) cudaFreeHost(ctx->h_info);
     ctx->arena.release();
     cudaStreamSynchronize(ctx->stream);
     delete ctx;
@@ -579,6 +616,25 @@ size_t later_b200_workspace_bytes(const later_b200_ctx* ctx, int m, int n) {
 }
 
 long later_b200_last_launch_count(const later_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int later_b200_last_info(later_b200_ctx* ctx, int* info) {
+    if (!ctx || !info) return LATER_B200_EINVAL;
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "sync");
+    info[0] = ctx->h_info[INFO_BAD_COLUMN];
+    info[1] = ctx->h_info[INFO_FLAGS];
+    info[2] = ctx->h_info[INFO_FALLBACKS];
+    info[3] = ctx->h_info[INFO_COND_LOG2];
+    return (info[0] != 0 || (info[1] & 1)) ? LATER_B200_ERANK : 0;
+}
+
+int later_b200_graph_stats(const later_b200_ctx* ctx, long* replays, long* captures) {
+    if (!ctx) return LATER_B200_EINVAL;
+    if (replays) *replays = ctx->graph_replays;
+    if (captures) *captures = ctx->graph_captures;
+    return 0;
+}
 
 int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
     return rgsqrf_device(ctx, m, n, A, lda, R, ldr);
@@ -622,7 +678,8 @@ int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda
                            int ldr) {
     int rc = validate(ctx, m, n, hA, lda, hR, ldr);
     if (rc) return rc;
-    cudaError_t e = cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = guard.error();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
     const size_t a_bytes = (size_t)m * n * sizeof(float), r_bytes = (size_t)n * n * sizeof(float);
     if (ctx->dA_bytes < a_bytes) {
@@ -639,6 +696,9 @@ int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda
     }
     if ((rc = rgsqrf_streamed(ctx, m, n, hA, lda, hR, ldr, ctx->dA, m, ctx->dR, n)) != 0) return rc;
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return cuda_fail(ctx, e, "sync");
+    // blocking call: the status words are in, so breakdown is reported right here
+    if (ctx->h_info[INFO_BAD_COLUMN] != 0 || (ctx->h_info[INFO_FLAGS] & 1))
+        return fail(ctx, LATER_B200_ERANK, rank_message(ctx->h_info));
     return 0;
 }
 
@@ -647,8 +707,8 @@ int later_b200_rgsqrf_stream_in(later_b200_ctx* ctx, int m, int n, const float* 
     int rc = validate(ctx, m, n, A, lda, R, ldr);
     if (rc) return rc;
     if (!hA || hlda < m) return fail(ctx, LATER_B200_EINVAL, "bad host matrix");
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    DeviceGuard guard(ctx->device);
+    if (guard.error() != cudaSuccess) return cuda_fail(ctx, guard.error(), "cudaSetDevice");
     return rgsqrf_streamed(ctx, m, n, const_cast<float*>(hA), hlda, nullptr, 0, A, lda, R, ldr);
 }
 
@@ -656,7 +716,8 @@ int later_b200_panel_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, fl
     if (!ctx) return LATER_B200_EINVAL;
     if (n != kPanelWidth) return fail(ctx, LATER_B200_EINVAL, "panel width must be 128");
     if (!A || !R || m < n || lda < m || ldr < n) return fail(ctx, LATER_B200_EINVAL, "bad panel arguments");
-    cudaError_t e = cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = guard.error();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
     const size_t bytes = panel_scratch_bytes(m, ctx->num_sms);
     if ((e = ctx->arena.reserve(bytes + 4096)) != cudaSuccess) {
@@ -666,9 +727,15 @@ int later_b200_panel_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, fl
     ctx->arena.reset();
     ctx->plan.valid = false;
     void* scratch = ctx->arena.alloc(bytes);
-    e = panel_qr128(ctx->stream, ctx->num_sms, m, A, lda, R, ldr, nullptr, 0, scratch, false);
-    ctx->launches = panel_launch_count(m, ctx->num_sms, A, lda, false);
+    if ((e = cudaMemsetAsync(ctx->d_info, 0, kInfoWords * sizeof(int), ctx->stream)) != cudaSuccess)
+        return cuda_fail(ctx, e, "info clear");
+    e = panel_qr128(ctx->stream, ctx->num_sms, m, A, lda, R, ldr, nullptr, 0, scratch, false, ctx->opts.panel,
+                    ctx->d_info, 0);
+    ctx->launches = panel_launch_count(m, ctx->num_sms, A, lda, false, ctx->opts.panel);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "panel_qr128");
+    if ((e = cudaMemcpyAsync(ctx->h_info, ctx->d_info, kInfoWords * sizeof(int), cudaMemcpyDeviceToHost,
+                             ctx->stream)) != cudaSuccess)
+        return cuda_fail(ctx, e, "info read-back");
     return 0;
 }
 
@@ -679,10 +746,12 @@ int later_b200_tsqr_apply(later_b200_ctx* ctx, int m, int n, float* Q, int ldq, 
     if (!p.valid || p.m != m || p.n != n || p.A != Q || p.lda != ldq)
         return fail(ctx, LATER_B200_ESTATE, "tsqr_apply needs the preceding rgsqrf on the same Q");
     if (!W || ldw < n) return fail(ctx, LATER_B200_EINVAL, "bad W");
-    cudaError_t e = cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = guard.error();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
-    cast_matrix_kernel<<<std::min(1184, (n * n + 255) / 256), 256, 0, ctx->stream>>>(W, ldw, n, n,
-                                                                                     p.Wh, n);
+    const long cast_blocks = std::min<long>(1184, ((long)n * n + 255) / 256);
+    cast_matrix_kernel<<<(unsigned)cast_blocks, 256, 0, ctx->stream>>>(W, ldw, n, n, p.Wh, n);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(ctx, e, "tsqr_apply cast");
     CUtensorMap q64, wmap;
     HalfMatrix qm{p.Qh, p.m, p.n, p.ldh}, wm{p.Wh, n, n, n};
     const int bn = n >= 256 ? 256 : 128;
@@ -702,7 +771,8 @@ int later_b200_gemm_gram(later_b200_ctx* ctx, const void* Qh, int q_rows, int q_
                          int colA, int Mc, int colB, int Nc, float* C, long ldc, void* Ch,
                          long ldch, int splits) {
     if (!ctx || !Qh || !C) return LATER_B200_EINVAL;
-    cudaError_t e = cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = guard.error();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
     const int bn = Nc >= 256 ? 256 : 128;
     if (splits <= 0) splits = choose_gram_splits(ctx->num_sms, Mc, Nc, bn, q_rows);
@@ -732,11 +802,11 @@ int later_b200_gemm_update(later_b200_ctx* ctx, const void* Qh, int q_rows, int 
                            int colA, int K, const void* Bh, long ldb, int Nc, float* C, long ldc,
                            void* Ch, long ldch, int subtract) {
     if (!ctx || !Qh || !Bh || !C) return LATER_B200_EINVAL;
-    cudaError_t e = cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = guard.error();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
     int bn = (Nc >= 256 && K >= 2048) ? 256 : 128;
-    int variant = 0;
-    if (const char* v = getenv("LB_UPDATE_VARIANT")) variant = atoi(v);   // diagnostics only
+    const int variant = ctx->opts.update_variant;   // diagnostics only
     if (variant == 1 || variant == 2) bn = Nc >= 256 ? 256 : 128;
     if (variant == 3) bn = 128;
     CUtensorMap q64, bmap;

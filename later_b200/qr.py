@@ -85,6 +85,21 @@ class Context:
     def workspace_bytes(self, m: int, n: int) -> int:
         return int(lib.later_b200_workspace_bytes(self._h, m, n))
 
+    def last_info(self) -> dict:
+        """Numerical status of the most recent factorisation (waits for the stream); see
+        later_b200_last_info in include/later_b200.h."""
+        arr = (C.c_int * 4)()
+        rc = lib.later_b200_last_info(self._h, arr)
+        if rc not in (0, -5):
+            self._raise(rc)
+        return {"status": rc, "bad_column": arr[0] - 1 if arr[0] else None, "nonfinite": bool(arr[1] & 1),
+                "fallback_panels": arr[2], "cond_log2": arr[3]}
+
+    def graph_stats(self) -> tuple[int, int]:
+        r, c = C.c_long(), C.c_long()
+        lib.later_b200_graph_stats(self._h, C.byref(r), C.byref(c))
+        return int(r.value), int(c.value)
+
 
 _default: dict[int, Context] = {}
 
@@ -148,6 +163,17 @@ def mgs_caqr_panel_256x128(ctxt: Context | None, m: int, n: int, A: torch.Tensor
     _check_colmajor("A", A, m, n, lda)
     _check_colmajor("R", R, n, n, ldr)
     rc = lib.later_b200_panel_qr(ctxt._h, m, n, A.data_ptr(), lda, R.data_ptr(), ldr)
+    if rc != 0:
+        ctxt._raise(rc)
+
+
+def mgs_caqr_panel_256x32(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int,
+                          R: torch.Tensor, ldr: int, work=None) -> None:
+    """QR of an m x 32 strip (reference QR/panel.cu:65-134)."""
+    ctxt = ctxt or default_context()
+    _check_colmajor("A", A, m, n, lda)
+    _check_colmajor("R", R, min(m, n), min(m, n), ldr)
+    rc = lib.later_b200_panel32_qr(ctxt._h, m, n, A.data_ptr(), lda, R.data_ptr(), ldr)
     if rc != 0:
         ctxt._raise(rc)
 

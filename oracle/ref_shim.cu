@@ -37,5 +37,16 @@ int ref_later_ormqr2(int m, int n, float* W, int ldw, float* Y, int ldy, float* 
     later_ormqr2(m, n, W, ldw, Y, ldy, work);
     return (int)cudaGetLastError();
 }
+int ref_mgs_caqr_panel_256x32(int m, int n, float* A, int lda, float* R, int ldr, float* work) {
+    ensure();
+    mgs_caqr_panel_256x32(g_ctxt, m, n, A, lda, R, ldr, work);
+    return (int)cudaGetLastError();
+}
+// the reference's 256 x 32 block kernel with the launch configuration of its callers
+// (QR/panel.cu:79,92,112): one (32, 32) block per 256 rows, R_b at rows 32 b of RR
+int ref_mgs_kernel2(int m, int n, float* A, int lda, float* RR, int ldr) {
+    mgs_kernel2<<<(m + 255) / 256, dim3(32, 32)>>>(m, n, A, lda, RR, ldr);
+    return (int)cudaGetLastError();
+}
 void ref_generate_uniform(float* dA, int m, int n) { generateUniformMatrix(dA, m, n); }
 }

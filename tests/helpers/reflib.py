@@ -1,0 +1,60 @@
+"""TEST INFRASTRUCTURE: ctypes binding of oracle/_ref/libref_later.so - the UNMODIFIED reference
+compiled by oracle/Makefile - so that GPU parity tests can run the reference beside the product on the
+same device buffer.  Only tests/ and bench.py's reference arm use it."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+PATH = ROOT / "oracle" / "_ref" / "libref_later.so"
+
+
+def available() -> bool:
+    return PATH.exists()
+
+
+class RefLib:
+    def __init__(self):
+        if not PATH.exists():
+            raise FileNotFoundError(f"{PATH} not built (oracle/Makefile needs /root/reference)")
+        self.lib = C.CDLL(str(PATH))
+        vp, ci = C.c_void_p, C.c_int
+        self.lib.ref_later_rgsqrf.argtypes = [ci, ci, vp, ci, vp, ci, vp, ci, vp, ci]
+        self.lib.ref_mgs_caqr_panel_256x128.argtypes = [ci, ci, vp, ci, vp, ci, vp]
+        for name in ("ref_mgs_caqr_panel_256x32",):
+            if hasattr(self.lib, name):
+                getattr(self.lib, name).argtypes = [ci, ci, vp, ci, vp, ci, vp]
+
+    @staticmethod
+    def _colmajor(x: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((x.shape[1], x.shape[0]), device="cuda", dtype=x.dtype).t()
+        out.copy_(x)
+        return out
+
+    def rgsqrf(self, A0: torch.Tensor):
+        """Reference later_rgsqrf on a copy of A0 (m x n, any layout); returns column-major Q, R."""
+        m, n = A0.shape
+        A = self._colmajor(A0)
+        R = torch.zeros((n, n), device="cuda", dtype=torch.float32).t()
+        work = torch.zeros(max(m // 256 * 32 * n, 1 << 20) + 4 * m + (1 << 20), device="cuda")
+        hwork = torch.zeros(m * n, device="cuda", dtype=torch.float16)
+        rc = self.lib.ref_later_rgsqrf(m, n, A.data_ptr(), m, R.data_ptr(), n, work.data_ptr(), work.numel(),
+                                       hwork.data_ptr(), hwork.numel())
+        torch.cuda.synchronize()
+        if rc != 0:
+            raise RuntimeError(f"reference later_rgsqrf: cuda error {rc}")
+        return A, R
+
+    def panel128(self, A0: torch.Tensor):
+        m, n = A0.shape
+        A = self._colmajor(A0)
+        R = torch.zeros((n, n), device="cuda", dtype=torch.float32).t()
+        work = torch.zeros(m * max(n, 32) + 65536, device="cuda")
+        rc = self.lib.ref_mgs_caqr_panel_256x128(m, n, A.data_ptr(), m, R.data_ptr(), n, work.data_ptr())
+        torch.cuda.synchronize()
+        if rc != 0:
+            raise RuntimeError(f"reference mgs_caqr_panel_256x128: cuda error {rc}")
+        return A, R
