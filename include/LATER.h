@@ -47,6 +47,13 @@ void later_rhouqr(cudaCtxt ctxt, int m, int n, float* A, int lda, float* W, int 
 void later_bhouqr(int m, int n, float* A, int lda, float* W, int ldw, float* R, int ldr,
                   float* work, int lwork, __half* hwork, int lhwork, float* U);
 
+// QDWH polar iteration, the reference's caller of later_rgsqrf (reference include/LATER.h:70,
+// EVD/later_qdwh_polar.cu:24-110): tmpA (n x n, ld n) holds the matrix and is normalised in place,
+// the top n x n block of A (2n x n, lda) receives the orthogonal polar factor.  H, work and hwork are
+// accepted and ignored (the reference never writes H).
+void later_qdwh_polar(cudaCtxt ctxt, int n, float* A, int lda, float* H, int ldh, float* tmpA, float* work,
+                      __half* hwork);
+
 // Utilities the reference driver calls (reference util/util.cu).
 void startTimer();
 float stopTimer();                                   // milliseconds since startTimer()
@@ -86,3 +93,5 @@ __global__ void s2h(int m, int n, float* as, int ldas, __half* ah, int ldah);
 __global__ void h2s(int m, int n, __half* ah, int ldah, float* as, int ldas);
 __global__ void setEye(int m, int n, float* a, int lda);
 __global__ void clearTri(char uplo, int m, int n, float* a, int lda);
+__global__ void deviceCopy(int m, int n, float* da, int lda, float* db, int ldb);          // db <- da
+__global__ void sSubstractAndSquare(int m, int n, float* dA, int lda, float* dB, int ldb);  // dB <- (dA - dB)^2

@@ -51,6 +51,25 @@ size_t later_b200_workspace_bytes(const later_b200_ctx* ctx, int m, int n);
  * Requirements: m >= n, n = 128 * 2^k (as in the reference), m a multiple of 8. */
 int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr);
 
+/* Gram-Schmidt twice (re-orthogonalisation): A = Q1 R1, Q1 = Q2 R2, A <- Q2, R <- R2 R1.  Same
+ * arguments and requirements as later_b200_rgsqrf; about twice its cost.  Use it when cond(A) is so
+ * large that one pass loses orthogonality (Gram-Schmidt with fp16 products: ~ cond * 5e-4, which is
+ * what the reference's driver checks for, reference test/test_qr.cu:91). */
+int later_b200_rgsqrf_reorth(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr);
+
+/* QDWH polar iteration, the reference's own caller of later_rgsqrf (reference
+ * EVD/later_qdwh_polar.cu:24-110): U <- orthogonal polar factor of X.
+ *   X (device, n x n, ldx)  in: the matrix; it is divided by its Frobenius norm in place and, as the
+ *                           reference does with its tmpA argument, left holding the last-but-one iterate
+ *   B (device, 2n x n, ldb >= 2n)  workspace for the stacked matrix [sqrt(c) X; I]; on return its top
+ *                           n x n block is U (the reference's A argument)
+ *   smin_est  lower bound of the smallest singular value of X / ||X||_F; <= 0 selects the constant the
+ *             reference hard-codes (0.0002070391384, EVD/later_qdwh_polar.cu:37)
+ *   max_iter  <= 0 selects the reference's 10;  iters (optional) <- iterations performed
+ * n = 128 * 2^k.  Blocks until done (the convergence test needs the host, as in the reference). */
+int later_b200_qdwh_polar(later_b200_ctx* ctx, int n, float* X, int ldx, float* B, int ldb, float smin_est,
+                          int max_iter, int* iters);
+
 /* Same with HOST buffers (what the reference's driver does by hand, test/test_qr.cu:47-56): A goes
  * to the device in column pieces of width max(128, n/16) and is factored left-looking, piece by
  * piece, as it arrives; every piece of Q and its columns of R travel back the moment they are

@@ -20,6 +20,9 @@ SYMBOLS = {
     "later_b200_set_graph": (C.c_int, [_c_ctx, C.c_int]),
     "later_b200_workspace_bytes": (C.c_size_t, [_c_ctx, C.c_int, C.c_int]),
     "later_b200_rgsqrf": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "later_b200_rgsqrf_reorth": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "later_b200_qdwh_polar": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float,
+                                        C.c_int, C.POINTER(C.c_int)]),
     "later_b200_rgsqrf_host": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "later_b200_rgsqrf_stream_in": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                               C.c_void_p, C.c_int]),

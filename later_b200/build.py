@@ -31,6 +31,7 @@ SOURCES = {
     "panel32.cu": ["-rdc=true"],
     "rgsqrf.cu": [],
     "ormqr.cu": [],
+    "qdwh.cu": [],
     "compat.cu": ["-rdc=true"],
 }
 

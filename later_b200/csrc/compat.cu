@@ -92,6 +92,12 @@ void later_ormqr2(int m, int n, float* W, int ldw, float* Y, int ldy, float*) {
     die_on(later_b200_ormqr2(default_ctx(), m, n, W, ldw, Y, ldy), "later_ormqr2");
 }
 
+void later_qdwh_polar(cudaCtxt, int n, float* A, int lda, float*, int, float* tmpA, float*, __half*) {
+    int iters = 0;
+    die_on(later_b200_qdwh_polar(default_ctx(), n, tmpA, n, A, lda, 0.f, 0, &iters), "later_qdwh_polar");
+    printf("later_qdwh_polar: %d iterations\n", iters);
+}
+
 void later_rhouqr(cudaCtxt, int, int, float*, int, float*, int, float*, int, float*, int, __half*,
                   int, float*) {
     fprintf(stderr, "later_rhouqr: Householder QR is out of scope of later_b200 (RGSQRF path only)\n");
@@ -184,4 +190,18 @@ __global__ void clearTri(char uplo, int m, int n, float* a, int lda) {
     if (i >= m || j >= n) return;
     const bool kill = (uplo == 'l') ? (i > j) : (i < j);
     if (kill) a[i + (long)j * lda] = 0.f;
+}
+
+__global__ void deviceCopy(int m, int n, float* da, int lda, float* db, int ldb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i < m && j < n) db[i + (long)j * ldb] = da[i + (long)j * lda];
+}
+
+__global__ void sSubstractAndSquare(int m, int n, float* dA, int lda, float* dB, int ldb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= m || j >= n) return;
+    const float d = dA[i + (long)j * lda] - dB[i + (long)j * ldb];
+    dB[i + (long)j * ldb] = d * d;
 }

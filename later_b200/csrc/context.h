@@ -76,11 +76,20 @@ struct later_b200_ctx {
     // device staging buffers for the *_host entry point
     float* dA = nullptr; size_t dA_bytes = 0;
     float* dR = nullptr; size_t dR_bytes = 0;
+    // scratch of the callers built on top of the factorisation (re-orthogonalisation, QDWH): lives
+    // outside the arena, which every factorisation carves anew
+    void* aux = nullptr; size_t aux_bytes = 0;
 };
 
 namespace lb {
 int fail(later_b200_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(later_b200_ctx* ctx, cudaError_t e, const char* where);
+
+// C = A * B, all fp32 column-major (A: M x K, B: K x N), fp32-faithful split-precision tcgen05
+// products (ormqr.cu).  M and K multiples of 8; scratch: split_gemm_scratch_bytes(M, N, K).
+size_t split_gemm_scratch_bytes(int M, int N, int K);
+int split_gemm_nn(later_b200_ctx* ctx, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
+                  float* C, long ldc, void* scratch, long* launches);
 
 // Makes the context's device current for the duration of a C-ABI call and restores the caller's.
 class DeviceGuard {

@@ -238,6 +238,47 @@ int ormqr_impl(later_b200_ctx* ctx, int m, int n, float* W, int ldw, const float
 }
 
 }  // namespace
+
+// C = A * B with every matrix fp32 column-major (A: M x K, B: K x N), fp32-faithful: the same
+// split-precision tcgen05 products as later_ormqr.  scratch must hold split_gemm_scratch_bytes.
+size_t split_gemm_scratch_bytes(int M, int N, int K) {
+    return 2 * round_up((size_t)round_up(M, 8) * K * sizeof(__half), 256) +
+           2 * round_up((size_t)round_up(K, 8) * N * sizeof(__half), 256) + 1024;
+}
+
+int split_gemm_nn(later_b200_ctx* ctx, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
+                  float* C, long ldc, void* scratch, long* launches) {
+    if (M % 8 != 0 || K % 8 != 0) return fail(ctx, LATER_B200_EINVAL, "split_gemm: M and K must be multiples of 8");
+    uint8_t* base = static_cast<uint8_t*>(scratch);
+    const long ldpa = round_up(M, 8), ldpb = round_up(K, 8);
+    const size_t pa = round_up((size_t)ldpa * K * sizeof(__half), 256), pb = round_up((size_t)ldpb * N * sizeof(__half), 256);
+    Planes Ap{(__half*)base, (__half*)(base + pa), ldpa};
+    Planes Bp{(__half*)(base + 2 * pa), (__half*)(base + 2 * pa + pb), ldpb};
+    float* scal = reinterpret_cast<float*>(base + 2 * pa + 2 * pb);
+    Ormqr o{};
+    o.ctx = ctx; o.st = ctx->stream;
+    o.kChunk = ctx->opts.ormqr_kchunk;
+    o.slot = reinterpret_cast<unsigned*>(scal + 32);
+    o.sW = scal; o.sY = scal + 2; o.sK = scal + 4; o.unscale = scal + 6;
+    o.check(cudaMemsetAsync(scal, 0, 64 * sizeof(float), o.st));
+    o.scale_of(A, lda, M, K, o.sW);
+    o.scale_of(B, ldb, K, N, o.sY);
+    o.split(A, lda, M, K, o.sW, Ap, false);
+    o.split(B, ldb, K, N, o.sY, Bp, false);
+    combine_scale_kernel<<<1, 1, 0, o.st>>>(o.sW, o.sY, o.unscale);
+    o.launches += 1;
+    const int bn = N >= 256 ? 256 : 128;
+    TcGemmParams p;
+    tc_fill_update(p, bn, 0, M, 0, K, 0, N, C, ldc, nullptr, 0);
+    o.product3(true, bn, HalfMatrix{Ap.hi, M, K, ldpa}, HalfMatrix{Ap.lo, M, K, ldpa}, HalfMatrix{Bp.hi, K, N, ldpb},
+               HalfMatrix{Bp.lo, K, N, ldpb}, p, EPI_STORE, EPI_ADD);
+    if (launches) *launches += o.launches;
+    if (o.err != cudaSuccess) return cuda_fail(ctx, o.err, "split_gemm");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "split_gemm launch");
+    return 0;
+}
+
 }  // namespace lb
 
 extern "C" {

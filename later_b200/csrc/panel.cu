@@ -488,6 +488,316 @@ chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
 }
 
 // ---------------------------------------------------------------------------------------------
+// R = chol(G)^T in fp64, one CTA, blocked (32-column blocks), synchronised with barriers only.
+//
+// Per block step b:
+//   warp 0          factors the 32 x 32 diagonal block entirely by itself: lane i owns row i in
+//                   registers, two columns per step (the two reciprocal square roots independent of
+//                   each other, as in chol_emit_pair), the column pair broadcast to the other lanes
+//                   through 512 bytes of shared memory behind a __syncwarp - ~200 cycles per pair
+//                   where the ring-and-poll protocol of chol128_kernel needs ~840
+//   warps 1 .. 11   meanwhile finish step b - 1: the rest of its trailing update and its output (32 rows
+//                   of R, the factor blocks of the apply kernel, 1/diag, the block-row flag)
+//   all             triangular solve of the rows below (one row per thread), then the update of the NEXT
+//                   diagonal block only, so that warp 0 can go on at once
+// Everything lives in shared memory (trailing matrix 129 KB, two block columns of L 65 KB).
+constexpr int CH2_THREADS = 384;
+constexpr int CH2_LDA = PW + 1;        // doubles per row of the trailing matrix (odd: rows hit distinct banks)
+constexpr int CH2_LDL = PW + 4;        // doubles per k-row of a block column of L: 16-byte aligned pairs, and the
+                                       // 4 k x 8 i elements of a DMMA fragment land in distinct banks
+struct Chol2Smem {
+    double As[PW][CH2_LDA];            // trailing matrix, As[i][j], i >= j
+    double Lt[2][GW][CH2_LDL];         // block column b of L in Lt[b & 1]: Lt[.][k][i] = L(i, 32 b + k)
+    double2 pair[2][GW];               // diagonal-block factorisation: the current column pair, per row
+    double rs[PW];                     // 1 / L(c, c)
+    double gdiag[PW];                  // G(c, c)
+    float Rs[GW][PW + 1];              // output staging: block-row b of R in fp32, Rs[k][i] = L(i, 32 b + k)
+    int bad;                           // 1 + local column of the first non-positive pivot (0 = none)
+#ifdef LB_CHOL_TRACE
+    long long tr[48];                  // phase timestamps (thread 0 / thread 32)
+#endif
+};
+#ifdef LB_CHOL_TRACE
+#define CH2_MARK(slot) do { if (tid == 0) s.tr[slot] = clock64(); } while (0)
+#define CH2_MARK1(slot) do { if (tid == 32) s.tr[slot] = clock64(); } while (0)
+#else
+#define CH2_MARK(slot) do {} while (0)
+#define CH2_MARK1(slot) do {} while (0)
+#endif
+
+// Warp 0: Cholesky of the diagonal block b.  Lane i owns row 32 b + i.
+__device__ __forceinline__ void chol2_diag_block(Chol2Smem& s, int b, int lane) {
+    const int o = GW * b;
+    double (*Lt)[CH2_LDL] = s.Lt[b & 1];
+    double a[GW];
+#pragma unroll
+    for (int j = 0; j < GW; ++j) a[j] = j <= lane ? s.As[o + lane][o + j] : 0.0;
+#pragma unroll
+    for (int kk = 0; kk < GW; kk += 2) {
+        const double piv0 = __shfl_sync(0xffffffffu, a[kk], kk);             // (c, c)
+        const double a10 = __shfl_sync(0xffffffffu, a[kk], kk + 1);          // (c+1, c)
+        const double a11 = __shfl_sync(0xffffffffu, a[kk + 1], kk + 1);      // (c+1, c+1)
+        // piv1 = a11 - a10^2 / piv0 = d / piv0: rsqrt(piv1) = rsqrt(d) sqrt(piv0), so the two reciprocal
+        // square roots start together
+        const double d = fma(a11, piv0, -a10 * a10);
+        const bool bad0 = !(piv0 > 0.0), bad1 = !(d > 0.0);
+        const double p0 = bad0 ? 1e-300 : piv0;
+        const double rs0 = rsqrt_f64(p0);
+        const double rd = rsqrt_f64(bad1 ? 1e-300 : d);
+        const double rs1 = rd * (p0 * rs0);
+        const double w = a10 * rs0 * rs0;                                    // L(c+1, c) / L(c, c)
+        double l0 = a[kk] * rs0;
+        double l1 = fma(-a[kk], w, a[kk + 1]) * rs1;
+        if (lane < kk) l0 = 0.0;
+        if (lane < kk + 1) l1 = 0.0;
+        s.pair[(kk >> 1) & 1][lane] = make_double2(l0, l1);
+        Lt[kk][o + lane] = l0;
+        Lt[kk + 1][o + lane] = l1;
+        if (lane == 0) {
+            s.rs[o + kk] = rs0;
+            s.rs[o + kk + 1] = rs1;
+            if (bad0 || bad1) atomicCAS(&s.bad, 0, o + kk + (bad0 ? 1 : 2));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = kk + 2; j < GW; ++j) {
+            const double2 lj = s.pair[(kk >> 1) & 1][j];                     // broadcast
+            a[j] = fma(-l1, lj.y, fma(-l0, lj.x, a[j]));
+        }
+    }
+}
+
+// Row i (below block b) of the block column: x L_bb^T = A(i, block b), right-looking in registers.
+__device__ __forceinline__ void chol2_trsm_row(Chol2Smem& s, int b, int i) {
+    const int o = GW * b;
+    double (*Lt)[CH2_LDL] = s.Lt[b & 1];
+    double x[GW];
+#pragma unroll
+    for (int j = 0; j < GW; ++j) x[j] = s.As[i][o + j];
+#pragma unroll
+    for (int k = 0; k < GW; ++k) {
+        const double xk = x[k] * s.rs[o + k];
+        x[k] = xk;
+        // L(o + j, o + k), j > k: broadcast loads, two entries each
+        if ((k & 1) == 0) x[k + 1] = fma(-xk, Lt[k][o + k + 1], x[k + 1]);
+#pragma unroll
+        for (int j = (k + 2) & ~1; j < GW; j += 2) {
+            const double2 l = *reinterpret_cast<const double2*>(&Lt[k][o + j]);
+            x[j] = fma(-xk, l.x, x[j]);
+            x[j + 1] = fma(-xk, l.y, x[j + 1]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < GW; ++k) Lt[k][i] = x[k];
+}
+
+// One 8 x 8 tile of the trailing update on the fp64 tensor path: A(i0.., j0..) -= L(i0.., :) L(j0.., :)^T over the
+// 32 columns of block column b (8 x mma.m8n8k4; fragments straight from Lt: A[r = lane / 4][k = lane % 4],
+// B[k = lane % 4][n = lane / 4], C[r = lane / 4][2 (lane % 4) + {0, 1}]).
+__device__ __forceinline__ void chol2_tile_update(Chol2Smem& s, const double (*Lt)[CH2_LDL], int i0, int j0, int lane) {
+    const int fr = lane >> 2, fk = lane & 3;
+    double* c = &s.As[i0 + fr][j0 + 2 * fk];
+    double acc[2] = {-c[0], -c[1]};                    // accumulate -A + L L^T, negate at the end
+#pragma unroll
+    for (int k = 0; k < GW; k += 4) dmma_884(acc, Lt[k + fk][i0 + fr], Lt[k + fk][j0 + fr]);
+    c[0] = -acc[0];
+    c[1] = -acc[1];
+}
+
+__device__ __forceinline__ void chol2_tile_update2(Chol2Smem& s, const double (*Lt)[CH2_LDL], int i0, int j0, int i1,
+                                                   int j1, int lane) {
+    const int fr = lane >> 2, fk = lane & 3;
+    double* c0 = &s.As[i0 + fr][j0 + 2 * fk];
+    double* c1 = &s.As[i1 + fr][j1 + 2 * fk];
+    double acc0[2] = {-c0[0], -c0[1]}, acc1[2] = {-c1[0], -c1[1]};
+#pragma unroll
+    for (int k = 0; k < GW; k += 4) {
+        dmma_884(acc0, Lt[k + fk][i0 + fr], Lt[k + fk][j0 + fr]);
+        dmma_884(acc1, Lt[k + fk][i1 + fr], Lt[k + fk][j1 + fr]);
+    }
+    c0[0] = -acc0[0]; c0[1] = -acc0[1];
+    c1[0] = -acc1[0]; c1[1] = -acc1[1];
+}
+
+// The next diagonal block only: A(i, j) -= sum_k L(i, k) L(j, k), i, j in block b + 1, j <= i: the ten lower
+// 8 x 8 tiles, one per warp.
+__device__ __forceinline__ void chol2_update_next_diag(Chol2Smem& s, int b, int warp, int lane) {
+    if (warp >= 10) return;
+    const int o = GW * (b + 1);
+    int ti = 0, t = warp;
+    while (t > ti) { t -= ti + 1; ++ti; }              // warp -> (ti, tj), tj <= ti
+    chol2_tile_update(s, s.Lt[b & 1], o + 8 * ti, o + 8 * t, lane);
+}
+
+// The rest of step b's trailing update (blocks (bi, bj), bi > b + 1, b + 1 <= bj <= bi), by warps 1 .. 11,
+// 8 x 8 tiles dealt round-robin (tiles above the diagonal of a diagonal block are skipped).
+__device__ __forceinline__ void chol2_update_rest(Chol2Smem& s, int b, int w, int lane) {
+    const double (*Lt)[CH2_LDL] = s.Lt[b & 1];
+    int unit = 0, pend_i = -1, pend_j = 0;             // two tiles at a time: independent DMMA chains
+    for (int bi = b + 2; bi < NGB; ++bi)
+        for (int bj = b + 1; bj <= bi; ++bj)
+            for (int ti = 0; ti < 4; ++ti)
+                for (int tj = 0; tj < 4; ++tj) {
+                    if (bi == bj && tj > ti) continue;
+                    if (unit++ % 11 != w) continue;
+                    const int i0 = GW * bi + 8 * ti, j0 = GW * bj + 8 * tj;
+                    if (pend_i < 0) { pend_i = i0; pend_j = j0; continue; }
+                    chol2_tile_update2(s, Lt, pend_i, pend_j, i0, j0, lane);
+                    pend_i = -1;
+                }
+    if (pend_i >= 0) chol2_tile_update(s, Lt, pend_i, pend_j, lane);
+}
+
+// Block-row b of R and everything the apply kernel needs from it, by the threads t = 0 .. nt - 1 of the
+// warps that do not factor the next diagonal block; ends with the block-row flag.  The block row is
+// rounded to fp32 into a staging array first (lanes along i: conflict-free), so that the global writes
+// can run along k (128 contiguous bytes per warp) without bank conflicts.
+__device__ __forceinline__ void chol2_output(Chol2Smem& s, int b, int t, int nt, const CholOut& o, int barrier_id) {
+    const int ob = GW * b;
+    const double (*Lt)[CH2_LDL] = s.Lt[b & 1];
+    for (int e = t; e < GW * PW; e += nt) {
+        const int i = e & (PW - 1), k = e >> 7;
+        s.Rs[k][i] = i < ob + k ? 0.f : (float)Lt[k][i];
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(nt) : "memory");
+    // R(k, i) = L(i, k), zero for i < k: lanes along k
+    for (int e = t; e < GW * PW; e += nt) {
+        const int k = e & 31, i = e >> 5;
+        o.R[ob + k + (long)i * o.ldr] = s.Rs[k][i];
+    }
+    // factor blocks [k][perm(c)]: lanes along i
+    for (int e = t; e < GW * (PW - ob); e += nt) {
+        const int c = e & 31, k = (e >> 5) & 31, j = b + (e >> 10);          // column block j >= b of R
+        const float v = s.Rs[k][GW * j + c];
+        if (j == b) o.fac->Rdiag[b][k][perm32(c)] = v;
+        else o.fac->Roff[off_index(b, j)][k][perm32(c)] = v;
+    }
+    if (t < GW) o.fac->rinv[ob + t] = (float)s.rs[ob + t];
+    // Publish: the barrier orders every thread's writes before thread 0's release store (release is
+    // cumulative over what the barrier made visible to it), so no thread needs a fence of its own -
+    // a __threadfence() per thread here stalled the whole CTA for thousands of cycles.
+    asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(nt) : "memory");
+    if (t == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(&o.fac->flag[b]), "r"(1) : "memory");
+}
+
+__global__ void __launch_bounds__(CH2_THREADS, 1)
+chol128b_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr, PanelFactors* __restrict__ fac,
+                int* __restrict__ info, int col0, int check_redo, double tau, const int* __restrict__ cond) {
+    extern __shared__ __align__(16) uint8_t chol2_raw[];
+    Chol2Smem& s = *reinterpret_cast<Chol2Smem*>(chol2_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const CholOut o{R, ldr, fac, info, col0, check_redo, tau};
+    if (tid == 0) s.bad = 0;
+    CH2_MARK(0);
+    pdl_wait();      // G and the cleared flags come from the reduce kernel
+    CH2_MARK(1);
+    if (cond) {      // fallback launch: runs only if the first attempt asked for it
+        if (*cond == 0) return;
+        if (tid == 0) { atomicAdd(&info[INFO_FALLBACKS], 1); atomicOr(&info[INFO_FLAGS], 2); }
+    }
+    // Only now may the dependent apply grid start: it synchronises on fac->flag[] (not on the
+    // completion of this grid), so the flags must already have been cleared by the reduce kernel.
+    pdl_trigger();
+    // G (upper 32 x 32 blocks [block][r][c]) -> lower triangle of As
+    {
+        constexpr int NLD = (GRAM_ELEMS + CH2_THREADS - 1) / CH2_THREADS;     // 27 loads per thread, all in flight
+        double v[NLD];
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int idx = tid + q * CH2_THREADS;
+            v[q] = idx < GRAM_ELEMS ? G[idx] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int idx = tid + q * CH2_THREADS;
+            if (idx < GRAM_ELEMS) {
+                // block t = idx >> 10 of the upper triangle -> (bi, bj), from two packed tables
+                const int t4 = (idx >> 10) * 4;
+                const int bi = (int)((0x3221110000ull >> t4) & 15), bj = (int)((0x3323213210ull >> t4) & 15);
+                const int j = GW * bi + ((idx >> 5) & 31), i = GW * bj + (idx & 31);
+                if (i >= j) {
+                    s.As[i][j] = v[q];
+                    if (i == j) s.gdiag[i] = v[q];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    CH2_MARK(2);
+#pragma unroll 1
+    for (int b = 0; b < NGB; ++b) {
+        if (warp == 0) {
+            chol2_diag_block(s, b, lane);
+            CH2_MARK(3 + 8 * b);
+        } else if (b > 0) {
+            chol2_update_rest(s, b - 1, warp - 1, lane);
+            CH2_MARK1(4 + 8 * b);
+            chol2_output(s, b - 1, tid - 32, CH2_THREADS - 32, o, 1);
+            CH2_MARK1(5 + 8 * b);
+        }
+        __syncthreads();
+        CH2_MARK(6 + 8 * b);
+        const int below = GW * (b + 1);
+        if (below + tid < PW) chol2_trsm_row(s, b, below + tid);
+#ifdef LB_CHOL_TRACE
+        asm volatile("" ::: "memory");
+        if (tid == 0) s.tr[36 + b] = clock64();
+        if (tid == 32) s.tr[40 + b] = clock64();
+        if (tid == 64) s.tr[44 + b] = clock64();
+        asm volatile("" ::: "memory");
+#endif
+        __syncthreads();
+        CH2_MARK(7 + 8 * b);
+        if (b + 1 < NGB) chol2_update_next_diag(s, b, warp, lane);
+        __syncthreads();
+        CH2_MARK(8 + 8 * b);
+    }
+    chol2_output(s, NGB - 1, tid, CH2_THREADS, o, 2);
+    CH2_MARK(35);
+#ifdef LB_CHOL_TRACE
+    __syncthreads();
+    if (tid == 0) {
+        const long long t0 = s.tr[0];
+        printf("chol2: pdl_wait %lld load %lld |", s.tr[1] - t0, s.tr[2] - s.tr[1]);
+        for (int b = 0; b < NGB; ++b) {
+            const long long start = b == 0 ? s.tr[2] : s.tr[8 * b];
+            printf(" b%d: diag %lld", b, s.tr[3 + 8 * b] - start);
+            if (b > 0) printf(" (rest %lld out %lld)", s.tr[4 + 8 * b] - start, s.tr[5 + 8 * b] - s.tr[4 + 8 * b]);
+            printf(" barA %lld trsm %lld upd %lld |", s.tr[6 + 8 * b] - start, s.tr[7 + 8 * b] - s.tr[6 + 8 * b],
+                   s.tr[8 + 8 * b] - s.tr[7 + 8 * b]);
+        }
+        printf(" final out %lld total %lld\n", s.tr[35] - s.tr[32], s.tr[35] - t0);
+        for (int b = 0; b < 3; ++b)
+            printf("  trsm b%d: warp0 %lld warp1 %lld warp2 %lld (from barA)\n", b, s.tr[36 + b] - s.tr[6 + 8 * b],
+                   s.tr[40 + b] - s.tr[6 + 8 * b], s.tr[44 + b] - s.tr[6 + 8 * b]);
+    }
+#endif
+    // Status of the panel.
+    if (warp == 0) {
+        double min_ratio = 1.0;
+#pragma unroll
+        for (int q = 0; q < PW / 32; ++q) {
+            const double rs = s.rs[lane + 32 * q], gd = s.gdiag[lane + 32 * q];
+            // piv / G_kk = 1 / (rs^2 G_kk); a zero or non-finite G_kk counts as breakdown
+            min_ratio = fmin(min_ratio, (gd > 0.0 && gd < 1e300) ? 1.0 / (rs * rs * gd) : 0.0);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) min_ratio = fmin(min_ratio, __shfl_xor_sync(0xffffffffu, min_ratio, off));
+        if (lane == 0) {
+            const int bad = s.bad;
+            if (check_redo) {
+                info[INFO_REDO] = (bad != 0 || !(min_ratio >= tau)) ? 1 : 0;
+            } else {
+                if (bad != 0) atomicCAS(&info[INFO_BAD_COLUMN], 0, col0 + bad);
+                int e = 0;
+                if (min_ratio > 0.0) { frexp(min_ratio, &e); e = 1 - e; } else { e = 2047; }
+                atomicMax(&info[INFO_COND_LOG2], e);      // ~ -log2(min ratio), rounded up
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Q = A R^-1.  128 rows per CTA, 128 threads: thread (rg, p) owns a 4-row x 8-column register tile -
 // rows 4 rg .. 4 rg + 3 and the columns c = p (mod 4) of the current 32-column block - so every
 // shared-memory operand it loads (4 q values, 8 R values, both as 16-byte loads) feeds 32 FMAs.
@@ -511,7 +821,7 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 
 __global__ void __launch_bounds__(APPLY_THREADS, 3)
 apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __restrict__ fac,
-                __half* __restrict__ Qh, long ldqh) {
+                __half* __restrict__ Qh, long ldqh, const int* __restrict__ only_if) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     ApplySmem& s = *reinterpret_cast<ApplySmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -523,6 +833,11 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
     const bool vec_a = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const bool vec_h = Qh && (ldqh % 4 == 0) && ((reinterpret_cast<uintptr_t>(Qh) & 7) == 0);
     pdl_trigger();   // (no pdl_wait: this grid synchronises with the Cholesky grid through flags)
+    if (only_if) {   // conditional launch behind the tensor-core apply of a tall panel: runs iff the panel
+                     // was factored again from the fp64 Gram matrix (every flag has long been raised)
+        pdl_wait();
+        if (*only_if == 0) return;
+    }
 
 #pragma unroll 1
     for (int jb = 0; jb < 4; ++jb) {
@@ -683,7 +998,20 @@ float* panel_colmax_scratch(void* scratch, int m, int num_sms) {
 cudaError_t panel_init() {
     cudaError_t e = cudaFuncSetAttribute(apply128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(ApplySmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(chol128b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chol2Smem));
     return e != cudaSuccess ? e : tc_apply_init();
+}
+
+// The panel's Cholesky factorisation: blocked barrier-synchronised kernel, or (LB_CHOL = 1, for
+// comparison) the register-resident ring-and-poll kernel of round 1.
+static cudaError_t launch_chol(cudaStream_t stream, const PanelOpts& opts, const double* G, float* R, long ldr,
+                               PanelFactors* fac, int* info, int col0, int check_redo, double tau, const int* cond) {
+    if (opts.chol_variant == 1)
+        return launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, G, R, ldr, fac, info, col0,
+                          check_redo, tau, cond);
+    return launch_pdl(chol128b_kernel, dim3(1), dim3(CH2_THREADS), sizeof(Chol2Smem), stream, G, R, ldr, fac, info,
+                      col0, check_redo, tau, cond);
 }
 
 bool panel_uses_i8_gram(int m, int num_sms, const float* A, long lda, bool allow_tc, const PanelOpts& opts) {
@@ -699,8 +1027,9 @@ bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc, const P
 }
 
 int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_tc, const PanelOpts& opts) {
-    return 4 + (panel_uses_tc_apply(m, A, lda, allow_tc, opts) ? 1 : 0) +
-           (panel_uses_i8_gram(m, num_sms, A, lda, allow_tc, opts) ? 4 : 0);
+    const bool tc = panel_uses_tc_apply(m, A, lda, allow_tc, opts);
+    const bool i8 = panel_uses_i8_gram(m, num_sms, A, lda, allow_tc, opts);
+    return 4 + (tc ? 1 : 0) + (i8 ? 4 : 0) + (i8 && tc ? 1 : 0);
 }
 
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
@@ -725,30 +1054,37 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
             return le;
         if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
                              igrid, G, fac->flag, never)) != cudaSuccess) return le;
-        if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr,
-                             fac, info, col0, 1, opts.i8_fallback_tau, never)) != cudaSuccess) return le;
+        if ((le = launch_chol(stream, opts, G, R, ldr, fac, info, col0, 1, opts.i8_fallback_tau, never)) != cudaSuccess)
+            return le;
         const int* redo = info + INFO_REDO;
         if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream, (const float*)A,
                              lda, m, part, redo)) != cudaSuccess) return le;
         if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
                              ggrid, G, fac->flag, redo)) != cudaSuccess) return le;
-        if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr,
-                             fac, info, col0, 0, 0.0, redo)) != cudaSuccess) return le;
+        if ((le = launch_chol(stream, opts, G, R, ldr, fac, info, col0, 0, 0.0, redo)) != cudaSuccess) return le;
     } else {
         if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream, (const float*)A,
                              lda, m, part, never)) != cudaSuccess) return le;
         if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
                              ggrid, G, fac->flag, never)) != cudaSuccess) return le;
-        if ((le = launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, (const double*)G, R, ldr,
-                             fac, info, col0, 0, 0.0, never)) != cudaSuccess) return le;
+        if ((le = launch_chol(stream, opts, G, R, ldr, fac, info, col0, 0, 0.0, never)) != cudaSuccess) return le;
     }
-    if (panel_uses_tc_apply(m, A, lda, allow_tc, opts))
-        return panel_apply_tc(stream, num_sms, m, A, lda, R, ldr, Qh, ldqh,
-                              reinterpret_cast<TcApplyFactors*>(base + L.tc_off));
-    // programmatic dependent launch: the apply grid may start while the Cholesky grid is running
     const PanelFactors* cfac = fac;
-    le = launch_pdl(apply128_kernel, dim3((m + APPLY_ROWS - 1) / APPLY_ROWS), dim3(APPLY_THREADS),
-                    sizeof(ApplySmem), stream, A, lda, m, cfac, Qh, ldqh);
+    const dim3 agrid((m + APPLY_ROWS - 1) / APPLY_ROWS);
+    if (panel_uses_tc_apply(m, A, lda, allow_tc, opts)) {
+        // a panel that was redone in fp64 (integer-Gram panels only) skips the tensor-core apply and
+        // is applied by forward substitution
+        const int* redone = panel_uses_i8_gram(m, num_sms, A, lda, allow_tc, opts) ? info + INFO_REDO : nullptr;
+        le = panel_apply_tc(stream, num_sms, m, A, lda, R, ldr, Qh, ldqh,
+                            reinterpret_cast<TcApplyFactors*>(base + L.tc_off), redone);
+        if (le != cudaSuccess || !redone) return le;
+        le = launch_pdl(apply128_kernel, agrid, dim3(APPLY_THREADS), sizeof(ApplySmem), stream, A, lda, m, cfac,
+                        Qh, ldqh, redone);
+        return le != cudaSuccess ? le : cudaGetLastError();
+    }
+    // programmatic dependent launch: the apply grid may start while the Cholesky grid is running
+    le = launch_pdl(apply128_kernel, agrid, dim3(APPLY_THREADS), sizeof(ApplySmem), stream, A, lda, m, cfac, Qh,
+                    ldqh, never);
     return le != cudaSuccess ? le : cudaGetLastError();
 }
 

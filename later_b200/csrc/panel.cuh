@@ -34,6 +34,7 @@ struct PanelOpts {
     // LB_I8_FALLBACK_TAU: an integer-Gram panel whose smallest Cholesky pivot ratio piv_k / G_kk falls
     // below this is factored again from the fp64 Gram matrix (see panel_qr128)
     double i8_fallback_tau = 0.0078125;
+    int chol_variant = 0;                    // LB_CHOL = 1: round 1's ring-and-poll Cholesky kernel (comparison only)
 };
 
 // Status words of a factorisation (device int[kInfoWords], cleared by the caller before the first
@@ -66,17 +67,21 @@ size_t panel_scratch_bytes(int m, int num_sms);
 // matrix drops digit pairs below 2^-26 of a product, a systematic error of ~1e-8 |G|, so
 // its panels are checked: if the smallest pivot ratio piv_k / G_kk (~ 1 / cond^2) is below
 // opts.i8_fallback_tau, or a pivot is not positive, the panel is factored AGAIN from the fp64 Gram
-// matrix.  The three fallback kernels are always enqueued (the launch sequence must not depend on
-// data: it is replayed from a CUDA graph) and exit at once unless the flag is set.  A non-positive
-// pivot on the fp64 path is clamped and reported in info[INFO_BAD_COLUMN].
+// matrix, and Q = A R^-1 is then formed by the fp32 forward substitution (row-wise backward stable)
+// instead of the tensor-core product with the explicit inverse, whose backward error grows with
+// cond(R) (measured at 131072 x 128, cond 1e6: 6e-7 against the reference's 1.5e-7).  The fallback
+// kernels are always enqueued (the launch sequence must not depend on data: it is replayed from a
+// CUDA graph) and exit at once unless the flag is set; the tensor-core apply exits at once if it is.
+// A non-positive pivot on the fp64 path is clamped and reported in info[INFO_BAD_COLUMN].
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
                         long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc,
                         const PanelOpts& opts, int* info, int col0, bool colmax_ready = false);
 
 cudaError_t panel_init();
 // Which kernels panel_qr128 will use (4 launches per panel with forward substitution, 5 with the
-// tensor-core apply: + the triangular inverse; + 4 or 5 with the integer Gram: column maxima unless
-// ready, the Gram kernel itself and the three conditional fallback kernels).
+// tensor-core apply: + the triangular inverse; + 5 or 6 with the integer Gram: column maxima unless
+// ready, the Gram kernel itself, the three conditional fallback kernels and the conditional
+// forward-substitution apply).
 bool panel_uses_tc_apply(int m, const float* A, long lda, bool allow_tc, const PanelOpts& opts);
 bool panel_uses_i8_gram(int m, int num_sms, const float* A, long lda, bool allow_tc, const PanelOpts& opts);
 int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_tc, const PanelOpts& opts);
@@ -103,7 +108,9 @@ cudaError_t panel_gram_i8(cudaStream_t stream, int num_sms, int m, const float* 
 float* panel_colmax_scratch(void* scratch, int m, int num_sms);
 // Q = A R^-1 for an m x 128 panel whose R (fp32, upper triangular) is already in place; needs
 // lda % 4 == 0 and a 16-byte aligned A.
+// skip (optional, device): when *skip != 0 both kernels return at once (the panel was factored again
+// from the fp64 Gram matrix and is applied by forward substitution).
 cudaError_t panel_apply_tc(cudaStream_t stream, int num_sms, int m, float* A, long lda, const float* R,
-                           long ldr, __half* Qh, long ldqh, TcApplyFactors* fac);
+                           long ldr, __half* Qh, long ldqh, TcApplyFactors* fac, const int* skip = nullptr);
 
 }  // namespace lb

@@ -81,7 +81,8 @@ __device__ __forceinline__ float pow2_scale(float x) {
 }
 
 __global__ void __launch_bounds__(TRINV_THREADS, 1)
-trinv128_kernel(const float* __restrict__ R, long ldr, TcApplyFactors* __restrict__ out) {
+trinv128_kernel(const float* __restrict__ R, long ldr, TcApplyFactors* __restrict__ out,
+                const int* __restrict__ skip) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     double* Ts = reinterpret_cast<double*>(smem_raw);                    // T(k, j) at k * TS_LD + j
     double* Rp = Ts + PW * TS_LD;                                        // R(i, k), i <= k, at k (k+1)/2 + i
@@ -92,6 +93,7 @@ trinv128_kernel(const float* __restrict__ R, long ldr, TcApplyFactors* __restric
     auto Rat = [&](int i, int k) -> double { return Rp[(k * (k + 1) >> 1) + i]; };
     pdl_trigger();
     pdl_wait();          // R comes from the Cholesky kernel
+    if (skip && *skip != 0) return;      // this panel is applied by forward substitution instead
 #ifdef LB_TRINV_TRACE
     long long tr[8]; int ntr = 0;
 #define TRINV_MARK() do { __syncthreads(); tr[ntr++] = clock64(); } while (0)
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1)
 apply128_tc_kernel(const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ CUtensorMap mapT2,
                    const __grid_constant__ CUtensorMap mapT3,
                    float* __restrict__ A, long lda, int m, const TcApplyFactors* __restrict__ fac,
-                   __half* __restrict__ Qh, long ldqh) {
+                   __half* __restrict__ Qh, long ldqh, const int* __restrict__ skip) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -253,7 +255,7 @@ apply128_tc_kernel(const __grid_constant__ CUtensorMap mapT1, const __grid_const
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tiles = (m + PW - 1) / PW;
+    int tiles = (m + PW - 1) / PW;
 
     if (warp == 8) {
         if (lane == 0) {
@@ -279,10 +281,12 @@ apply128_tc_kernel(const __grid_constant__ CUtensorMap mapT1, const __grid_const
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_trigger();
     pdl_wait();          // T planes, scales (trinv kernel) and A (whatever produced the panel)
+    const bool skipped = skip && *skip != 0;     // the panel is applied by forward substitution instead
+    if (skipped) tiles = 0;
 
     if (warp == 8) {
         // ------------------------------------------------------------------ T loader + MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && !skipped) {
             mbar_arrive_expect_tx(t_full, T_BYTES);
             for (int kb = 0; kb < 2; ++kb) {
                 tma_load_2d(t_base + kb * KB_BYTES, &mapT1, t_full, kb * 64, 0);
@@ -713,8 +717,8 @@ cudaError_t tc_apply_init() {
 }
 
 cudaError_t panel_apply_tc(cudaStream_t stream, int num_sms, int m, float* A, long lda, const float* R,
-                           long ldr, __half* Qh, long ldqh, TcApplyFactors* fac) {
-    cudaError_t e = launch_pdl(trinv128_kernel, dim3(1), dim3(TRINV_THREADS), TRINV_SMEM, stream, R, ldr, fac);
+                           long ldr, __half* Qh, long ldqh, TcApplyFactors* fac, const int* skip) {
+    cudaError_t e = launch_pdl(trinv128_kernel, dim3(1), dim3(TRINV_THREADS), TRINV_SMEM, stream, R, ldr, fac, skip);
     if (e != cudaSuccess) return e;
     CUtensorMap t1, t2, t3;
     HalfMatrix m1{fac->T[0], PW, PW, PW}, m2{fac->T[1], PW, PW, PW}, m3{fac->T[2], PW, PW, PW};
@@ -724,7 +728,7 @@ cudaError_t panel_apply_tc(cudaStream_t stream, int num_sms, int m, float* A, lo
     const int tiles = (m + PW - 1) / PW;
     const int grid = tiles < num_sms ? tiles : num_sms;
     e = launch_pdl(apply128_tc_kernel, dim3(grid), dim3(TCA_THREADS), (size_t)TCA_SMEM, stream, t1, t2, t3, A,
-                   lda, m, (const TcApplyFactors*)fac, Qh, ldqh);
+                   lda, m, (const TcApplyFactors*)fac, Qh, ldqh, skip);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -505,6 +505,7 @@ void read_options(Options& o) {
     o.panel.gram_i8 = geti("LB_GRAM_I8", 1) != 0;
     o.panel.gram_i8_min_rows = geti("LB_GRAM_I8_MIN_ROWS", kI8GramMinRows);
     if (const char* v = getenv("LB_I8_FALLBACK_TAU")) o.panel.i8_fallback_tau = atof(v);
+    o.panel.chol_variant = geti("LB_CHOL", 0);
     o.gram_cast = geti("LB_GRAM_CAST", 1) != 0;
     o.update_variant = geti("LB_UPDATE_VARIANT", 0);
     o.ormqr_kchunk = std::max(64, geti("LB_ORMQR_KCHUNK", 2048) / 64 * 64);
@@ -592,6 +593,7 @@ int later_b200_destroy(later_b200_ctx* ctx) {
         if (ev) cudaEventDestroy(ev);
     if (ctx->dA) cudaFree(ctx->dA);
     if (ctx->dR) cudaFree(ctx->dR);
+    if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     ctx->arena.release();
@@ -638,6 +640,36 @@ int later_b200_graph_stats(const later_b200_ctx* ctx, long* replays, long* captu
 
 int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
     return rgsqrf_device(ctx, m, n, A, lda, R, ldr);
+}
+
+// Gram-Schmidt twice ("CGS2-style" re-orthogonalisation): A = Q1 R1, Q1 = Q2 R2,
+// R = R2 R1.  The second pass sees an almost orthonormal matrix, so its orthogonality no longer
+// depends on cond(A): for the price of a second factorisation and one triangular product (fp32-faithful
+// split-precision tcgen05 GEMMs) the result is orthogonal to the fp16 level of a well-conditioned input.
+int later_b200_rgsqrf_reorth(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
+    int rc = validate(ctx, m, n, A, lda, R, ldr);
+    if (rc) return rc;
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = guard.error();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    const size_t nn = (size_t)n * n;
+    const size_t need = 2 * nn * sizeof(float) + split_gemm_scratch_bytes(n, n, n) + 256;
+    if (ctx->aux_bytes < need) {
+        if (ctx->aux) cudaFree(ctx->aux);
+        ctx->aux = nullptr; ctx->aux_bytes = 0;
+        if ((e = cudaMalloc(&ctx->aux, need)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc scratch");
+        ctx->aux_bytes = need;
+    }
+    float* R1 = static_cast<float*>(ctx->aux);
+    float* R2 = R1 + nn;
+    void* scratch = R2 + nn;
+    if ((rc = rgsqrf_device(ctx, m, n, A, lda, R1, n)) != 0) return rc;
+    long launches = ctx->launches;
+    if ((rc = rgsqrf_device(ctx, m, n, A, lda, R2, n)) != 0) return rc;
+    launches += ctx->launches;
+    rc = split_gemm_nn(ctx, n, n, n, R2, n, R1, n, R, ldr, scratch, &launches);
+    ctx->launches = launches;
+    return rc;
 }
 
 // Shared by the two host-input entry points: factor the device matrix (dA, dR) while its columns

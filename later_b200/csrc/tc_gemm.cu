@@ -499,6 +499,7 @@ cudaError_t tc_gemm_init() {
     LB_SET(128, true, EPI_SUB) LB_SET(256, true, EPI_SUB)
     LB_SET(128, true, EPI_STORE) LB_SET(256, true, EPI_STORE)
     LB_SET(128, false, EPI_ADD) LB_SET(256, false, EPI_ADD)
+    LB_SET(128, true, EPI_ADD) LB_SET(256, true, EPI_ADD)
 #undef LB_SET
     if ((e = cudaFuncSetAttribute(tc_gram2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg2<256>::SMEM_BYTES)) != cudaSuccess)
@@ -532,6 +533,7 @@ cudaError_t tc_gemm_launch(cudaStream_t stream, int num_sms, bool a_mn_major, in
     LB_CASE(128, false, EPI_ADD) LB_CASE(256, false, EPI_ADD)
     LB_CASE(128, true, EPI_SUB) LB_CASE(256, true, EPI_SUB)
     LB_CASE(128, true, EPI_STORE) LB_CASE(256, true, EPI_STORE)
+    LB_CASE(128, true, EPI_ADD) LB_CASE(256, true, EPI_ADD)
 #undef LB_CASE
     return cudaErrorInvalidValue;
 }

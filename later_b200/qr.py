@@ -124,6 +124,34 @@ def later_rgsqrf(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int
         ctxt._raise(rc)
 
 
+def later_rgsqrf_reorth(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int, R: torch.Tensor,
+                        ldr: int) -> None:
+    """Gram-Schmidt twice: A = Q1 R1, Q1 = Q2 R2; A <- Q2, R <- R2 R1 (include/later_b200.h)."""
+    ctxt = ctxt or default_context()
+    _check_colmajor("A", A, m, n, lda)
+    _check_colmajor("R", R, n, n, ldr)
+    rc = lib.later_b200_rgsqrf_reorth(ctxt._h, m, n, A.data_ptr(), lda, R.data_ptr(), ldr)
+    if rc != 0:
+        ctxt._raise(rc)
+
+
+def later_qdwh_polar(ctxt: Context | None, n: int, A: torch.Tensor, lda: int, H, ldh: int, tmpA: torch.Tensor,
+                     work=None, hwork=None, smin_est: float = 0.0, max_iter: int = 0) -> int:
+    """Polar factor by the QDWH iteration (reference EVD/later_qdwh_polar.cu:24-110), with the
+    reference's argument list: tmpA (n x n, ld n) holds the matrix (normalised in place), A (2n x n,
+    lda) is the stacked workspace whose top block receives U; H, work and hwork are accepted and
+    ignored (the reference never writes H either).  Returns the number of iterations."""
+    ctxt = ctxt or default_context()
+    _check_colmajor("tmpA", tmpA, n, n, tmpA.stride(1))
+    _check_colmajor("A", A, 2 * n, n, lda)
+    it = C.c_int(0)
+    rc = lib.later_b200_qdwh_polar(ctxt._h, n, tmpA.data_ptr(), tmpA.stride(1), A.data_ptr(), lda,
+                                   float(smin_est), int(max_iter), C.byref(it))
+    if rc != 0:
+        ctxt._raise(rc)
+    return int(it.value)
+
+
 def later_rgsqrf_host(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int,
                       R: torch.Tensor, ldr: int) -> None:
     """Same with HOST (ideally pinned) buffers; H2D and D2H copies happen inside the call, overlapped

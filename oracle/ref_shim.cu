@@ -48,5 +48,11 @@ int ref_mgs_kernel2(int m, int n, float* A, int lda, float* RR, int ldr) {
     mgs_kernel2<<<(m + 255) / 256, dim3(32, 32)>>>(m, n, A, lda, RR, ldr);
     return (int)cudaGetLastError();
 }
+// reference later_qdwh_polar (EVD/later_qdwh_polar.cu:24): tmpA (n x n) in, top block of A (2n x n) out
+int ref_later_qdwh_polar(int n, float* A, int lda, float* tmpA, float* work, void* hwork) {
+    ensure();
+    later_qdwh_polar(g_ctxt, n, A, lda, nullptr, n, tmpA, work, (__half*)hwork);
+    return (int)cudaGetLastError();
+}
 void ref_generate_uniform(float* dA, int m, int n) { generateUniformMatrix(dA, m, n); }
 }

@@ -11,6 +11,7 @@ rounded to fp16 with round-to-nearest, fp32 accumulation):
     mgs_caqr_panel_256x32()   QR/panel.cu:65-134           TSQR tree over 256-row blocks
     mgs_kernel2()             QR/panel.cu:246-325          256 x 32 modified Gram-Schmidt
     later_ormqr/_ormqr2()     QR/later_ormqr.cu:18-85      explicit Q from WY
+    later_qdwh_polar()        EVD/later_qdwh_polar.cu:24-110  QDWH polar iteration, the caller of later_rgsqrf
     check_result/check_otho   test/test_qr.cu:216-268      the driver's self-consistency metrics
 
 Third-party arithmetic: every GEMM on the path is cuBLAS (closed source; 12.9.1.4 in this image;
@@ -153,6 +154,49 @@ def later_ormqr(W: np.ndarray, Y: np.ndarray) -> np.ndarray:
     work = _gemm_f32(Y[:, :h].T, W[:, h:])
     W[:, h:] -= _gemm_f32(W[:, :h], work)
     return later_ormqr2(W, Y)
+
+
+def later_qdwh_polar(X0: np.ndarray, smin_est: float = 0.0002070391384, max_iter: int = 10):
+    """QDWH polar iteration as EVD/later_qdwh_polar.cu:24-110 runs it: normalise by the Frobenius norm
+    (:26-31), L = smin_est / sqrt(n) with the reference's hard-coded smin_est (:37-38), then per
+    iteration the dynamically weighted Halley coefficients (:60-66), RGSQRF of the stacked
+    [sqrt(c) X; I] (:71-79), X <- (a - b/c)/sqrt(c) * fp16(Q1) fp16(Q2)^T + (b/c) X (:86-98) and
+    the symmetrisation (X + X^T)/2 (:100, generateNewU :10-21 - restated as the averaging it is
+    meant to be: the kernel itself races between thread blocks).  Stops as :53-57 does.
+    Returns (U, iterations)."""
+    X = np.array(X0, dtype=F32, order="F", copy=True)
+    n = X.shape[0]
+    X *= F32(1.0) / F32(np.sqrt(np.sum(X.astype(np.float64) ** 2)))
+    L = F32(smin_est) / F32(np.sqrt(F32(n)))
+    eps = F32(2e-4)
+    tol1 = F32(10.0) * eps / F32(2.0)
+    tol3 = F32(tol1 ** (1.0 / 3.0))
+    prev = None
+    it = 0
+    for it in range(max_iter):
+        if it > 0:
+            diff = np.sqrt(np.sum((prev.astype(np.float64) - X.astype(np.float64)) ** 2))
+            if diff < tol3 and F32(1.0) - L < tol1:
+                break
+        L2 = F32(L * L)
+        dd = F32((F32(4.0) * (1 - L2) / (L2 * L2)) ** (1.0 / 3.0))
+        sqd = F32(np.sqrt(1 + dd))
+        a = F32(sqd + np.sqrt(8 - 4 * dd + 8 * (2 - L2) / (L2 * sqd)) / 2)
+        b = F32((a - 1) * (a - 1) / 4)
+        c = F32(a + b - 1)
+        # clamped at 1 (mathematically L <= 1; the reference's fp32 update can overshoot by an ulp, after
+        # which its coefficients are NaN - the clamp is the one deliberate deviation of this restatement)
+        L = F32(min(F32(L * (a + b * L2) / (1 + c * L2)), F32(1.0)))
+        B = np.empty((2 * n, n), dtype=F32, order="F")
+        B[:n] = X * F32(np.sqrt(c))
+        B[n:] = np.eye(n, dtype=F32)
+        Q, _ = later_rgsqrf(B)
+        W = _gemm_tc(s2h(Q[:n]), s2h(Q[n:]).T) * F32((a - b / c) / np.sqrt(c)) + F32(b / c) * X
+        prev = X
+        X = (F32(0.5) * (W + W.T)).astype(F32)
+    else:
+        it = max_iter
+    return X, it
 
 
 def check_result(A: np.ndarray, Q: np.ndarray, R: np.ndarray) -> float:

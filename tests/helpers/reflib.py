@@ -28,6 +28,20 @@ class RefLib:
             if hasattr(self.lib, name):
                 getattr(self.lib, name).argtypes = [ci, ci, vp, ci, vp, ci, vp]
 
+    def qdwh_polar(self, X0: torch.Tensor) -> torch.Tensor:
+        """Reference later_qdwh_polar (EVD/later_qdwh_polar.cu:24) on a copy of X0 (n x n); returns U."""
+        n = X0.shape[0]
+        self.lib.ref_later_qdwh_polar.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        tmpA = self._colmajor(X0)
+        A = torch.zeros((n, 2 * n), device="cuda", dtype=torch.float32).t()          # 2n x n, lda = 2n
+        work = torch.zeros(max(n * n, 2 * n // 256 * 32 * n) + (1 << 20), device="cuda")
+        hwork = torch.zeros(2 * n * n, device="cuda", dtype=torch.float16)
+        rc = self.lib.ref_later_qdwh_polar(n, A.data_ptr(), 2 * n, tmpA.data_ptr(), work.data_ptr(), hwork.data_ptr())
+        torch.cuda.synchronize()
+        if rc != 0:
+            raise RuntimeError(f"reference later_qdwh_polar: cuda error {rc}")
+        return A[:n].clone()
+
     @staticmethod
     def _colmajor(x: torch.Tensor) -> torch.Tensor:
         out = torch.empty((x.shape[1], x.shape[0]), device="cuda", dtype=x.dtype).t()

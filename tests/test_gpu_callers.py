@@ -1,0 +1,164 @@
+"""The rows SURVEY.md par.8 marks "next": the QDWH polar iteration (the reference's own caller of
+later_rgsqrf, EVD/later_qdwh_polar.cu:24-110) and the re-orthogonalisation option, each against the
+oracle on small inputs and against the UNMODIFIED reference (oracle/_ref/libref_later.so) run beside
+the product on the same device buffers."""
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from oracle import rgsqrf_oracle as orc  # noqa: E402
+from tests.helpers import reflib  # noqa: E402
+from tests.helpers.inputs import cond_matrix, metrics  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qr():
+    from later_b200 import qr as _qr
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _qr
+
+
+@pytest.fixture(scope="module")
+def ctx(qr):
+    c = qr.Context()
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return reflib.RefLib() if reflib.available() else None
+
+
+def _sym_uniform(n, seed):
+    """The input of the reference's driver (test/test_qdwh_polar.cu:53-59): U(0,1], symmetrised."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    H = torch.rand(n, n, device="cuda", generator=g)
+    return 0.5 * (H + H.t())
+
+
+def _polar_fp64(H):
+    U, _, Vh = torch.linalg.svd(H.double())
+    return U @ Vh
+
+
+# ------------------------------------------------------------------------------ the call site's shape
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_rgsqrf_on_the_stacked_qdwh_matrix_vs_reference(qr, ctx, ref, n):
+    """later_rgsqrf on [sqrt(c) X; I] (2n x n), the matrix EVD/later_qdwh_polar.cu:71-79 hands it in its
+    first iteration (c ~ 1e6 for the reference's smin estimate: the top block dominates)."""
+    X = _sym_uniform(n, 41)
+    X = X / torch.linalg.norm(X)
+    B0 = torch.cat([X * math.sqrt(1.0e6), torch.eye(n, device="cuda")], dim=0)
+    A = qr.to_colmajor(B0)
+    R = qr.colmajor_empty(n, n)
+    qr.later_rgsqrf(ctx, 2 * n, n, A, 2 * n, R, n)
+    assert ctx.last_info()["status"] == 0
+    back, orth = metrics(B0, A, R)
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_later.so not built")
+    Qr, Rr = ref.rgsqrf(B0)
+    if not torch.isfinite(Qr).all():
+        # The reference's CAQR panel factors every 256-row block on its own (QR/panel.cu:87-93); inside the
+        # identity block most 256 x 32 blocks hold all-zero columns, whose norm it divides by
+        # (QR/panel.cu:286-290): NaN from n = 512 on.  The Gram/Cholesky panel works on whole columns.
+        assert back <= 5e-4 and orth <= 5e-3, (back, orth)
+        return
+    back_ref, orth_ref = metrics(B0, Qr, Rr)
+    assert back <= 2 * back_ref + 1e-7 and orth <= 2 * orth_ref + 1e-8, (back, back_ref, orth, orth_ref)
+
+
+# ------------------------------------------------------------------------------ QDWH
+def test_qdwh_polar_vs_oracle(qr, ctx):
+    n = 256
+    H = _sym_uniform(n, 42)
+    Uo, it_o = orc.later_qdwh_polar(H.cpu().numpy())
+    tmpA = qr.to_colmajor(H)
+    A = qr.colmajor_empty(2 * n, n)
+    it = qr.later_qdwh_polar(ctx, n, A, 2 * n, None, n, tmpA)
+    U = A[:n].cpu().numpy()
+    Ue = _polar_fp64(H).cpu().numpy()
+    assert it == it_o
+    err, err_o = np.abs(U - Ue).max(), np.abs(Uo - Ue).max()
+    assert err <= 2 * err_o + 1e-4, (err, err_o)
+    assert np.abs(U - Uo).max() <= 2 * err_o + 1e-4
+    assert np.abs(U - U.T).max() == 0.0                       # symmetrised exactly
+
+
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_qdwh_polar_vs_reference(qr, ctx, ref, n):
+    """Same input, the reference's own constants (smin estimate, 10 iterations at most): the polar factor
+    must be as close to the fp64 one, and as orthogonal, as the reference's (within 2x)."""
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_later.so not built")
+    H = _sym_uniform(n, 43)
+    Ue = _polar_fp64(H)
+    Ur = ref.qdwh_polar(H)
+    tmpA = qr.to_colmajor(H)
+    A = qr.colmajor_empty(2 * n, n)
+    it = qr.later_qdwh_polar(ctx, n, A, 2 * n, None, n, tmpA)
+    U = A[:n]
+    assert 2 <= it <= 10
+    eye = torch.eye(n, device="cuda", dtype=torch.float64)
+
+    def quality(V):
+        return (float(torch.linalg.norm(V.double() - Ue) / math.sqrt(n)),
+                float(torch.linalg.norm(V.double().t() @ V.double() - eye) / n))
+    err, orth = quality(U)
+    if not torch.isfinite(Ur).all():
+        # (see above: the reference's own factorisation of [sqrt(c) X; I] breaks down from n = 512 on - its
+        # driver, test/test_qdwh_polar.cu:72, has the call commented out)
+        # Without a reference answer: U must be orthogonal to the fp16 level of the factorisations, and
+        # close to the fp64 polar factor except along the near-null directions of this input (its
+        # smallest singular values are ~1e-6 of the largest; the polar factor moves by O(perturbation /
+        # sigma_min) there), hence the loose forward bound.
+        assert orth <= 2e-4, (err, orth)
+        assert err <= 0.3, (err, orth)
+        return
+    err_r, orth_r = quality(Ur)
+    assert err <= 2 * err_r + 1e-5 and orth <= 2 * orth_r + 1e-6, (err, err_r, orth, orth_r)
+
+
+# ------------------------------------------------------------------------------ re-orthogonalisation
+def test_reorth_vs_oracle(qr, ctx):
+    rng = np.random.default_rng(44)
+    m, n = 1024, 256
+    A0 = (rng.standard_normal((m, n)) * np.logspace(0, -3, n)).astype(np.float32) @ \
+        np.linalg.qr(rng.standard_normal((n, n)))[0].astype(np.float32)
+    A = qr.to_colmajor(torch.from_numpy(A0).cuda())
+    R = qr.colmajor_empty(n, n)
+    R.fill_(float("nan"))
+    qr.later_rgsqrf_reorth(ctx, m, n, A, m, R, n)
+    Q, R = A.cpu().numpy(), R.cpu().numpy()
+    Q1, R1 = orc.later_rgsqrf(A0)
+    Q2, R2 = orc.later_rgsqrf(Q1)
+    Ro = (R2.astype(np.float64) @ R1.astype(np.float64)).astype(np.float32)
+    assert np.abs(np.tril(R, -1)).max() == 0.0 and (np.diag(R) > 0).all()
+    assert orc.check_otho(Q) <= 2 * orc.check_otho(Q2) + 1e-7
+    assert orc.check_result(A0, Q, R) <= 2 * orc.check_result(A0, Q2, Ro) + 1e-7
+    assert orc.check_otho(Q) <= 0.1 * orc.check_otho(Q1)      # that is the point of the second pass
+
+
+@pytest.mark.parametrize("m,n,kappa", [(16384, 1024, 1e3), (131072, 1024, 1e4)])
+def test_reorth_restores_orthogonality(qr, ctx, m, n, kappa):
+    A0 = cond_matrix(m, n, kappa, seed=45)
+    A1 = qr.to_colmajor(A0)
+    R1 = qr.colmajor_empty(n, n)
+    qr.later_rgsqrf(ctx, m, n, A1, m, R1, n)
+    back1, orth1 = metrics(A0, A1, R1)
+    A2 = qr.to_colmajor(A0)
+    R2 = qr.colmajor_empty(n, n)
+    qr.later_rgsqrf_reorth(ctx, m, n, A2, m, R2, n)
+    assert ctx.last_info()["status"] == 0
+    back2, orth2 = metrics(A0, A2, R2)
+    assert torch.tril(R2, -1).abs().max().item() == 0.0
+    assert orth2 <= 5e-5 and orth2 <= 0.05 * orth1, (orth1, orth2)
+    assert back2 <= 2 * back1 + 1e-6, (back1, back2)

@@ -117,3 +117,20 @@ def test_fp16_cast_is_round_to_nearest_even():
     x = np.array([1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, 65504.0, 1e-8], dtype=np.float32)
     h = orc.s2h(x).astype(np.float32)
     assert h[0] == 1.0 and h[1] == np.float32(1.0 + 2.0 ** -9) and h[2] == 65504.0 and h[3] == 0.0
+
+
+def test_oracle_qdwh_polar_converges_to_the_polar_factor():
+    """later_qdwh_polar (EVD/later_qdwh_polar.cu:24-110) restated: on the driver's kind of input
+    (symmetric U(0,1], test/test_qdwh_polar.cu:53-59) the iteration must reach the orthogonal polar
+    factor to the fp16 level of the factorisations it is built on, in a handful of steps."""
+    from scipy.linalg import polar
+    rng = np.random.default_rng(7)
+    n = 128
+    H = rng.random((n, n), dtype=np.float32)
+    H = 0.5 * (H + H.T)
+    U, iters = orc.later_qdwh_polar(H)
+    Ue, _ = polar(H.astype(np.float64))
+    assert 2 <= iters <= 10
+    assert np.abs(U - Ue).max() <= 5e-2
+    assert np.linalg.norm(U.astype(np.float64).T @ U - np.eye(n)) / n <= 1e-4
+    assert np.abs(U - U.T).max() == 0.0
