@@ -7,8 +7,10 @@ reference prints (reference test/test_qr.cu:85-86).
 N = 1 : 16384 x 16384 on one B200 (BASELINE.json configs[1]).  The line also carries a `configs`
         block with the other single-GPU configurations (1024^2 on the reference's own cuRAND input,
         262144 x 256, 1048576 x 1024, 32768^2 + later_ormqr), each measured in the same run.
-N > 1 : 1048576 x 1024, row-sharded over N GPUs, TSQR combine (configs[3]); launched by
-        torch.distributed.run, one rank per GPU, NCCL.  Strong scaling (total work fixed).  Every
+N > 1 : 1048576 x 1024, row-sharded over N GPUs (configs[3]); launched by torch.distributed.run, one
+        rank per GPU, NCCL.  Every rank runs the same recursion on its row block with the panel Gram
+        matrices and the R12 blocks all-reduced (later_b200_rgsqrf_dist); the classical TSQR variant
+        (local QR, all-gather of R, stack QR, back-multiply) is timed beside it.  Strong scaling.  Every
         rank generates ITS ROWS OF THE SAME GLOBAL MATRIX (a generator keyed by the global element
         index), so the N-GPU factorisation is checked globally (backward error, orthogonality,
         all-reduced) and compared with a 1-GPU run of the very same matrix made by rank 0 in-run.
@@ -349,7 +351,7 @@ def main():
         workload = "rgsqrf_16384x16384_square"
     else:
         m, n = 1048576, 1024
-        workload = f"rgsqrf_1048576x1024_rowsharded_tsqr_dp{N}"
+        workload = f"rgsqrf_1048576x1024_rowsharded_dp{N}"
     if args.m and args.n:
         m, n = args.m, args.n
         workload = f"rgsqrf_{m}x{n}_override"
@@ -375,13 +377,20 @@ def main():
     if args.impl == "b200":
         from later_b200 import qr
         from later_b200.tsqr import tsqr_rgsqrf
+        if distributed:
+            # The library's NCCL collectives get a non-blocking stream of their own: on the legacy default
+            # stream they would synchronise implicitly with every blocking stream of the process.
+            work_stream = torch.cuda.Stream()
+            torch.cuda.set_stream(work_stream)
         ctx_main, ctx_stack = qr.Context(), qr.Context()
+        if distributed:
+            qr.comm_init(ctx_main)                 # the library's own NCCL communicator over the ranks
 
         def step():
             nonlocal launches_per_step
             if distributed:
-                tsqr_rgsqrf(m_loc, n, A, m_loc, R, n, ctxs=(ctx_main, ctx_stack))
-                launches_per_step = 2 * ctx_main.last_launch_count + ctx_stack.last_launch_count
+                qr.later_rgsqrf_dist(ctx_main, m_loc, n, A, m_loc, R, n)
+                launches_per_step = ctx_main.last_launch_count
             else:
                 qr.later_rgsqrf(ctx_main, m_loc, n, A, m_loc, R, n)
                 launches_per_step = ctx_main.last_launch_count
@@ -472,7 +481,7 @@ def main():
     if distributed:
         # ---- per-GPU roofline of the sharded step (HBM-bound: SURVEY.md par.8d)
         gbs = algorithmic_bytes(m_loc, n) / (ms_per_step * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "whole sharded step, per GPU (local QR + stack QR + back-multiply)",
+        line["roofline"] = {"bound": "hbm", "kernel": "whole sharded step, per GPU (row-sharded recursion incl. its all-reduces)",
                             "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                             "traffic": None, "bytes_per_gpu": algorithmic_bytes(m_loc, n),
                             "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs"}
@@ -493,6 +502,29 @@ def main():
             del T0, T, Rt, G1
             torch.cuda.empty_cache()
         dist.broadcast(anchor, 0)
+        # ---- the classical TSQR variant on the same shards, for comparison (fp16 back-multiplication)
+        ctx_t = qr.Context()
+        T = torch.empty((n, m_loc), device="cuda").t()
+        Rt = torch.zeros((n, n), device="cuda").t()
+        ts = []
+        for i in range(6):
+            T.copy_(A0)
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); tsqr_rgsqrf(m_loc, n, T, m_loc, Rt, n, ctxs=(ctx_t, ctx_stack)); e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        t_tsqr = torch.tensor([sorted(ts)[1]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t_tsqr, op=dist.ReduceOp.MAX)
+        r2, n2, Gt = chunked_metrics(torch, A0, T, Rt)
+        dist.all_reduce(r2); dist.all_reduce(n2); dist.all_reduce(Gt)
+        Gt.diagonal().sub_(1.0)
+        line["tsqr_variant"] = {"ms_per_step": float(t_tsqr.item()), "backward_error": float(torch.sqrt(r2 / n2)),
+                                "orthogonality": float(torch.linalg.norm(Gt)) / n,
+                                "what": "local QR + all-gather of R + redundant stack QR + fp16 back-multiplication"}
+        del T, Rt, Gt
+        ctx_t.close()
         line["one_gpu_same_matrix"] = {"ms_per_step": float(anchor[0]), "backward_error": float(anchor[2]),
                                        "max_rel_diff_R_vs_sharded": float(anchor[1])}
         line["speedup_vs_1gpu"] = float(anchor[0]) / ms_per_step
@@ -560,9 +592,8 @@ def main():
             barrier()
             t0 = time.perf_counter()
             if distributed:
-                # the row block crosses PCIe while the local factorisation already runs on the
-                # columns that have arrived; Q leaves after the TSQR back-multiplication
-                tsqr_rgsqrf(m_loc, n, A, m_loc, R, n, ctxs=(ctx_main, ctx_stack), host_A=hA0.t())
+                A.t().copy_(hA0, non_blocking=True)
+                qr.later_rgsqrf_dist(ctx_main, m_loc, n, A, m_loc, R, n)
                 hA.copy_(A.t(), non_blocking=True)
                 hR.copy_(R.t(), non_blocking=True)
                 barrier()
@@ -583,7 +614,7 @@ def main():
                        "d2h_bytes_per_step": 4 * (m_loc * n + r_back) * shards,
                        "ms_per_step": float(t_e2e.item()) * 1e3,
                        "step_ms": [t * 1e3 for t in times],
-                       "api": ("tsqr_rgsqrf(host_A=pinned) + D2H of Q and R" if distributed else
+                       "api": ("H2D of the row block + later_rgsqrf_dist + D2H of Q and R (pinned buffers)" if distributed else
                                "later_rgsqrf_host (pinned host A in, Q and R out)")}
         if distributed:
             # what the box's host side gives when every rank copies at once and nothing computes: the

@@ -104,6 +104,45 @@ int later_b200_panel32_qr(later_b200_ctx* ctx, int m, int n, float* A, int lda, 
 int later_b200_tsqr_apply(later_b200_ctx* ctx, int m, int n, float* Q, int ldq, const float* W,
                           int ldw);
 
+/* ---- row-sharded factorisation, one rank per GPU (SURVEY.md par.8 e; the reference is single-GPU) ----
+ * Rank p owns the row block A_p (m_local x n) of the global (P m_local) x n matrix.
+ * later_b200_rgsqrf_dist runs the SAME recursion as later_b200_rgsqrf on it, with the Gram matrix of
+ * every 128-column panel (fp64) and every R12 = Q1^T A2 block (fp32) summed over the ranks by an NCCL
+ * all-reduce (15 small collectives for n = 1024), so that every rank factors the global matrix: on
+ * return A_p holds its rows of the global Q and R the global R, identical on all ranks.  Same
+ * accuracy as the single-GPU factorisation, 1/P of its work per rank.  Collective: all ranks must call
+ * it with the same n; asynchronous on the context's stream.  NCCL is loaded at run time
+ * (libnccl.so.2); a process that already uses NCCL (PyTorch) shares its copy.
+ *   one process per GPU:   rank 0 calls later_b200_comm_unique_id, sends the 128 bytes to the others by
+ *                          whatever means it has; every rank calls later_b200_comm_init
+ *   one process, P GPUs:   later_b200_comm_init_all over the P contexts (one host thread per context
+ *                          then calls later_b200_rgsqrf_dist, or see later_b200_rgsqrf_mgpu below) */
+#define LATER_B200_COMM_ID_BYTES 128
+int later_b200_comm_unique_id(void* id128);
+int later_b200_comm_init(later_b200_ctx* ctx, int nranks, int rank, const void* id128);
+int later_b200_comm_init_all(later_b200_ctx* const* ctxs, int nranks);
+int later_b200_rgsqrf_dist(later_b200_ctx* ctx, int m_local, int n, float* A, int lda, float* R, int ldr);
+
+/* ---- row-sharded tall-skinny QR over the GPUs of one node, one host thread ----------------------
+ * (SURVEY.md par.8 e; the reference is single-GPU.)  Device p owns the row block A[p] (m_local x n,
+ * column-major, lda) of the global (P m_local) x n matrix.  On return A[p] holds its rows of the global
+ * Q and R[p] (device p, n x n, ldr) the global R - bit-identical on every device.  One NCCL all-gather
+ * of the P local R factors is the only communication (libnccl.so.2 is loaded at run time, P > 1 only).
+ * The call is asynchronous on the handle's per-device streams; later_b200_mgpu_sync waits for all. */
+typedef struct later_b200_mgpu later_b200_mgpu;
+int later_b200_mgpu_create(later_b200_mgpu** out, int P, const int* devices);
+int later_b200_mgpu_destroy(later_b200_mgpu* g);
+int later_b200_tsqr_mgpu(later_b200_mgpu* g, int m_local, int n, float* const* A, int lda, float* const* R,
+                         int ldr);
+/* Same arguments, the row-sharded recursion (later_b200_rgsqrf_dist on every device, one host thread
+ * each inside the call): the preferred form - reference-level accuracy and no redundant work.
+ * later_b200_tsqr_mgpu keeps the classical TSQR structure (local QR, one all-gather of the R factors,
+ * redundant stack QR, fp16 back-multiplication: backward error at fp16 level). */
+int later_b200_rgsqrf_mgpu(later_b200_mgpu* g, int m_local, int n, float* const* A, int lda, float* const* R,
+                           int ldr);
+int later_b200_mgpu_sync(later_b200_mgpu* g);
+const char* later_b200_mgpu_last_error(const later_b200_mgpu* g);
+
 /* Explicit Q from a Householder WY pair.  Replaces later_ormqr (reference include/LATER.h:43,
  * QR/later_ormqr.cu:18-64): W[:, n/2:] -= W[:, :n/2] * (Y[:, :n/2]^T W[:, n/2:]), then
  * W <- I - W * Y[0:n, 0:n]^T.  fp32-faithful (split-precision tensor-core products). */

@@ -36,6 +36,18 @@ SYMBOLS = {
     "later_b200_gemm_update": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int,
                                          C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long, C.c_void_p,
                                          C.c_long, C.c_int]),
+    "later_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "later_b200_comm_init": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p]),
+    "later_b200_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "later_b200_rgsqrf_dist": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "later_b200_rgsqrf_mgpu": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                         C.POINTER(C.c_void_p), C.c_int]),
+    "later_b200_mgpu_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int)]),
+    "later_b200_mgpu_destroy": (C.c_int, [C.c_void_p]),
+    "later_b200_tsqr_mgpu": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                       C.POINTER(C.c_void_p), C.c_int]),
+    "later_b200_mgpu_sync": (C.c_int, [C.c_void_p]),
+    "later_b200_mgpu_last_error": (C.c_char_p, [C.c_void_p]),
     "later_b200_last_launch_count": (C.c_long, [_c_ctx]),
     "later_b200_last_info": (C.c_int, [_c_ctx, C.POINTER(C.c_int)]),
     "later_b200_graph_stats": (C.c_int, [_c_ctx, C.POINTER(C.c_long), C.POINTER(C.c_long)]),

@@ -32,6 +32,7 @@ SOURCES = {
     "rgsqrf.cu": [],
     "ormqr.cu": [],
     "qdwh.cu": [],
+    "mgpu.cu": [],
     "compat.cu": ["-rdc=true"],
 }
 
@@ -77,7 +78,7 @@ def build(force: bool = False, verbose: bool = False, defines: list[str] | None 
         if p.returncode != 0:
             sys.stderr.write(out.decode())
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc(), "-shared", *ARCH, *objs, "-o", str(LIB), "-lcurand",
+    link = [nvcc(), "-shared", *ARCH, *objs, "-o", str(LIB), "-lcurand", "-ldl",
             "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     if verbose:
         print(" ".join(link), flush=True)

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "arena.h"
+#include "nccl_dl.h"
 #include "panel.cuh"
 
 namespace lb {
@@ -47,6 +48,8 @@ struct later_b200_ctx {
         float* part = nullptr; size_t part_floats = 0;
         void* panel_scratch = nullptr;
         unsigned long arena_gen = 0;
+        bool dist = false;                        // row-sharded factorisation (all-reduces inside)
+        float* stage = nullptr;                   // its contiguous R12 staging block (n/2 x n/2 fp32)
         // host buffers of later_b200_rgsqrf_host (null for the device entry points): the copies are
         // part of that call's graph, so they are part of its identity
         float* hA = nullptr; long hlda = 0;
@@ -65,7 +68,7 @@ struct later_b200_ctx {
         long launches = 0;
         bool seen = false;      // plan was launched directly once; capture on the next identical call
         unsigned long tick = 0; // last use (LRU)
-    } graphs[2][lb::kGraphSlots];
+    } graphs[3][lb::kGraphSlots];      // [2]: the row-sharded factorisation (NCCL all-reduces captured with it)
     unsigned long graph_tick = 0;
     long graph_replays = 0, graph_captures = 0;   // counters (tests)
 
@@ -76,6 +79,10 @@ struct later_b200_ctx {
     // device staging buffers for the *_host entry point
     float* dA = nullptr; size_t dA_bytes = 0;
     float* dR = nullptr; size_t dR_bytes = 0;
+    // communicator of the row-sharded factorisation (later_b200_comm_init / _comm_init_all)
+    lb::Nccl* nccl = nullptr;
+    lb::ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
     // scratch of the callers built on top of the factorisation (re-orthogonalisation, QDWH): lives
     // outside the arena, which every factorisation carves anew
     void* aux = nullptr; size_t aux_bytes = 0;

@@ -730,9 +730,11 @@ chol128b_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr, P
             chol2_diag_block(s, b, lane);
             CH2_MARK(3 + 8 * b);
         } else if (b > 0) {
-            chol2_update_rest(s, b - 1, warp - 1, lane);
-            CH2_MARK1(4 + 8 * b);
+            // (output first: the apply kernel, which is already running, gets its block row ~4000
+            // cycles earlier; the update only has to be done by the next barrier)
             chol2_output(s, b - 1, tid - 32, CH2_THREADS - 32, o, 1);
+            CH2_MARK1(4 + 8 * b);
+            chol2_update_rest(s, b - 1, warp - 1, lane);
             CH2_MARK1(5 + 8 * b);
         }
         __syncthreads();
@@ -762,7 +764,7 @@ chol128b_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr, P
         for (int b = 0; b < NGB; ++b) {
             const long long start = b == 0 ? s.tr[2] : s.tr[8 * b];
             printf(" b%d: diag %lld", b, s.tr[3 + 8 * b] - start);
-            if (b > 0) printf(" (rest %lld out %lld)", s.tr[4 + 8 * b] - start, s.tr[5 + 8 * b] - s.tr[4 + 8 * b]);
+            if (b > 0) printf(" (out %lld rest %lld)", s.tr[4 + 8 * b] - start, s.tr[5 + 8 * b] - s.tr[4 + 8 * b]);
             printf(" barA %lld trsm %lld upd %lld |", s.tr[6 + 8 * b] - start, s.tr[7 + 8 * b] - s.tr[6 + 8 * b],
                    s.tr[8 + 8 * b] - s.tr[7 + 8 * b]);
         }
@@ -1034,7 +1036,7 @@ int panel_launch_count(int m, int num_sms, const float* A, long lda, bool allow_
 
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
                         long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc,
-                        const PanelOpts& opts, int* info, int col0, bool colmax_ready) {
+                        const PanelOpts& opts, int* info, int col0, bool colmax_ready, const PanelComm* comm) {
     const ScratchLayout L = scratch_layout(m, num_sms);
     uint8_t* base = static_cast<uint8_t*>(scratch);
     double* part = reinterpret_cast<double*>(base + L.part_off);
@@ -1043,6 +1045,10 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
     const int ggrid = gram_grid(m, num_sms);
     const int rgrid = (GRAM_ELEMS + 31) / 32;
     const int* never = nullptr;
+    // row-sharded factorisation: G becomes the Gram matrix of the global panel (sum over ranks)
+    auto global_sum = [&]() -> cudaError_t {
+        return comm ? comm->allreduce_f64(comm->self, G, GRAM_ELEMS, stream) : cudaSuccess;
+    };
 
     cudaError_t le;
     if (panel_uses_i8_gram(m, num_sms, A, lda, allow_tc, opts)) {
@@ -1054,6 +1060,7 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
             return le;
         if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
                              igrid, G, fac->flag, never)) != cudaSuccess) return le;
+        if ((le = global_sum()) != cudaSuccess) return le;
         if ((le = launch_chol(stream, opts, G, R, ldr, fac, info, col0, 1, opts.i8_fallback_tau, never)) != cudaSuccess)
             return le;
         const int* redo = info + INFO_REDO;
@@ -1061,12 +1068,16 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
                              lda, m, part, redo)) != cudaSuccess) return le;
         if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
                              ggrid, G, fac->flag, redo)) != cudaSuccess) return le;
+        // (unconditional - the launch sequence is static: when the panel was not redone this sums a stale G
+        // that the skipped Cholesky launch below never reads)
+        if ((le = global_sum()) != cudaSuccess) return le;
         if ((le = launch_chol(stream, opts, G, R, ldr, fac, info, col0, 0, 0.0, redo)) != cudaSuccess) return le;
     } else {
         if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream, (const float*)A,
                              lda, m, part, never)) != cudaSuccess) return le;
         if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
                              ggrid, G, fac->flag, never)) != cudaSuccess) return le;
+        if ((le = global_sum()) != cudaSuccess) return le;
         if ((le = launch_chol(stream, opts, G, R, ldr, fac, info, col0, 0, 0.0, never)) != cudaSuccess) return le;
     }
     const PanelFactors* cfac = fac;

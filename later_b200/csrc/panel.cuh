@@ -49,6 +49,14 @@ enum PanelInfo : int {
     INFO_REDO = 4,         // scratch: "factor this panel again" flag between the two Cholesky launches
 };
 
+// Collective hook of the row-sharded (multi-GPU) factorisation: sums `count` doubles in place over all
+// ranks, on `stream`.  With it the panel's Gram matrix is the Gram matrix of the GLOBAL panel, and every
+// rank derives the same R from it.
+struct PanelComm {
+    void* self;
+    cudaError_t (*allreduce_f64)(void* self, double* buf, size_t count, cudaStream_t stream);
+};
+
 // Scratch (bytes) needed by panel_qr128 for an m-row panel on a device with num_sms SMs.
 size_t panel_scratch_bytes(int m, int num_sms);
 
@@ -75,7 +83,8 @@ size_t panel_scratch_bytes(int m, int num_sms);
 // A non-positive pivot on the fp64 path is clamped and reported in info[INFO_BAD_COLUMN].
 cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long lda, float* R,
                         long ldr, __half* Qh, long ldqh, void* scratch, bool allow_tc,
-                        const PanelOpts& opts, int* info, int col0, bool colmax_ready = false);
+                        const PanelOpts& opts, int* info, int col0, bool colmax_ready = false,
+                        const PanelComm* comm = nullptr);
 
 cudaError_t panel_init();
 // Which kernels panel_qr128 will use (4 launches per panel with forward substitution, 5 with the

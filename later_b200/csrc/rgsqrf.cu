@@ -77,7 +77,7 @@ __global__ void cast_shadow_kernel(const float* __restrict__ A, long lda, int m,
 }
 
 struct Workspace {
-    size_t qh_bytes, r12h_bytes, wh_bytes, part_bytes, panel_bytes, total;
+    size_t qh_bytes, r12h_bytes, wh_bytes, part_bytes, panel_bytes, stage_bytes, total;
     long ldh;
 };
 
@@ -89,7 +89,7 @@ int gram_bn(int h) { return h >= 512 ? 256 : 128; }
 int update_bn(int h) { return h >= 4096 ? 256 : 128; }
 bool update_uses_tma(int h) { return h < 4096 || h >= 8192; }
 
-Workspace plan_workspace(int num_sms, int m, int n) {
+Workspace plan_workspace(int num_sms, int m, int n, bool dist = false) {
     Workspace w{};
     w.ldh = round_up(m, 8);
     w.qh_bytes = (size_t)w.ldh * n * sizeof(__half);
@@ -102,8 +102,9 @@ Workspace plan_workspace(int num_sms, int m, int n) {
     w.part_bytes = part;
     w.panel_bytes = panel_scratch_bytes(m, num_sms);
     w.wh_bytes = (size_t)n * n * sizeof(__half);  // fp16 W of the TSQR back-multiplication
+    w.stage_bytes = dist && n > NMIN ? (size_t)(n / 2) * (n / 2) * sizeof(float) : 0;   // all-reduce staging of R12
     w.total = round_up(w.qh_bytes, 256) + round_up(w.r12h_bytes, 256) + round_up(w.wh_bytes, 256) +
-              round_up(w.part_bytes, 256) + round_up(w.panel_bytes, 256) + 4096;
+              round_up(w.part_bytes, 256) + round_up(w.panel_bytes, 256) + round_up(w.stage_bytes, 256) + 4096;
     return w;
 }
 
@@ -195,6 +196,35 @@ struct HostPipe {
     }
 };
 
+// Row-sharded factorisation: the all-reduced R12 block leaves its contiguous staging buffer for R
+// (fp32, ld ldr), for the fp16 operand of the update, and the mirror block is cleared.
+__global__ void finish_r12_kernel(const float* __restrict__ S, int h, int nb, float* __restrict__ R12, long ldr,
+                                  __half* __restrict__ R12h, long ldh, float* __restrict__ Z) {
+    const long total = (long)h * nb;
+    pdl_trigger();
+    pdl_wait();
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % h), j = (int)(idx / h);
+        const float v = S[idx];
+        R12[i + (long)j * ldr] = v;
+        R12h[i + (long)j * ldh] = __float2half_rn(v);
+        if (Z) Z[i + (long)j * ldr] = 0.f;
+    }
+}
+
+cudaError_t comm_allreduce(later_b200_ctx* ctx, void* buf, size_t count, int dtype, cudaStream_t stream) {
+    if (!ctx->comm || !ctx->nccl) return cudaErrorNotReady;
+    const ncclResult_t r = ctx->nccl->AllReduce(buf, buf, count, dtype, kNcclSum, ctx->comm, stream);
+    if (r != 0) {
+        ctx->error = std::string("ncclAllReduce: ") + ctx->nccl->GetErrorString(r);
+        return cudaErrorUnknown;
+    }
+    return cudaSuccess;
+}
+cudaError_t comm_allreduce_f64(void* self, double* buf, size_t count, cudaStream_t stream) {
+    return comm_allreduce(static_cast<later_b200_ctx*>(self), buf, count, kNcclDouble, stream);
+}
+
 struct Recursion {
     later_b200_ctx* ctx;
     later_b200_ctx::Plan* p;
@@ -213,9 +243,11 @@ struct Recursion {
         if (w <= NMIN) {
             const bool ready = colmax_col == c0;
             colmax_col = -1;
+            const PanelComm comm{ctx, comm_allreduce_f64};
             check(panel_qr128(st, ctx->num_sms, p->m, p->A + (long)c0 * p->lda, p->lda,
                               p->R + c0 + (long)c0 * p->ldr, p->ldr, p->Qh + (long)c0 * p->ldh,
-                              p->ldh, p->panel_scratch, true, ctx->opts.panel, ctx->d_info, c0, ready));
+                              p->ldh, p->panel_scratch, true, ctx->opts.panel, ctx->d_info, c0, ready,
+                              p->dist ? &comm : nullptr));
             launches += panel_launch_count(p->m, ctx->num_sms, p->A + (long)c0 * p->lda, p->lda, true,
                                            ctx->opts.panel) - (ready ? 1 : 0);
         } else {
@@ -247,18 +279,32 @@ struct Recursion {
         float* R12 = p->R + c0 + (long)cb * p->ldr;
         // (the mirror block R21, which the algorithm never produces, is written as zero on the way)
         float* Z = zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr;
+        // Row-sharded: this rank's product is only its share of R12 = sum over ranks of Q1_p^T A2_p.  It goes
+        // to a contiguous staging block, is summed over the ranks (NCCL all-reduce, fp32) and only then
+        // leaves for R and for the fp16 operand of the update - every rank continues with the same R12.
+        float* C = p->dist ? p->stage : R12;
+        const long ldc = p->dist ? h : p->ldr;
+        __half* Ch = p->dist ? nullptr : p->R12h;
+        float* Zk = p->dist ? nullptr : Z;
         const bool fused = b_is_input && ctx->opts.gram_cast && splits >= 2 && tc_gram_cast_supports(h) &&
                            p->m >= kTcApplyMinRows && p->lda % 4 == 0 &&
                            (reinterpret_cast<uintptr_t>(p->A) & 15) == 0;
         if (fused) {
             check(tc_gram_cast(st, ctx->num_sms, q128, p->m, c0, h, p->A + (long)cb * p->lda, p->lda, nb,
-                               R12, p->ldr, p->R12h, h, p->part, splits, Z));
+                               C, ldc, Ch, h, p->part, splits, Zk));
         } else {
             if (b_is_input) cast(cb, cb + nb);
-            check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, cb, nb, R12,
-                          p->ldr, p->R12h, h, p->part, splits, Z));
+            check(tc_gram(st, ctx->num_sms, q128, bn == 256 ? q256 : q128, bn, 0, p->m, c0, h, cb, nb, C,
+                          ldc, Ch, h, p->part, splits, Zk));
         }
         launches += splits > 1 ? 2 : 1;
+        if (p->dist) {
+            check(comm_allreduce(ctx, p->stage, (size_t)h * nb, kNcclFloat, st));
+            const int blocks = (int)std::min<long>(((long)h * nb + 255) / 256, 148L * 8);
+            check(launch_pdl(finish_r12_kernel, dim3(blocks), dim3(256), 0, st, (const float*)p->stage, h, nb, R12,
+                             (long)p->ldr, p->R12h, (long)h, Z));
+            launches += 1;
+        }
         CUtensorMap r12map;
         HalfMatrix rm{p->R12h, h, nb, h};
         const int ubn = nb % 256 == 0 ? update_bn(h) : 128;
@@ -337,8 +383,8 @@ int validate(later_b200_ctx* ctx, int m, int n, const void* A, int lda, const vo
 }
 
 // Reserves and carves the workspace for (m, n); fills ctx->plan.
-int prepare_plan(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
-    const Workspace w = plan_workspace(ctx->num_sms, m, n);
+int prepare_plan(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr, bool dist = false) {
+    const Workspace w = plan_workspace(ctx->num_sms, m, n, dist);
     cudaError_t e = ctx->arena.reserve(w.total);
     if (e != cudaSuccess) {
         cuda_fail(ctx, e, "workspace reserve");
@@ -355,8 +401,11 @@ int prepare_plan(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R,
     p.part = w.part_bytes ? static_cast<float*>(ctx->arena.alloc(w.part_bytes)) : nullptr;
     p.part_floats = w.part_bytes / sizeof(float);
     p.panel_scratch = ctx->arena.alloc(w.panel_bytes);
+    p.dist = dist;
+    p.stage = w.stage_bytes ? static_cast<float*>(ctx->arena.alloc(w.stage_bytes)) : nullptr;
     p.arena_gen = ctx->arena.generation();
-    p.valid = p.Qh && p.Wh && p.panel_scratch && (!w.r12h_bytes || p.R12h) && (!w.part_bytes || p.part);
+    p.valid = p.Qh && p.Wh && p.panel_scratch && (!w.r12h_bytes || p.R12h) && (!w.part_bytes || p.part) &&
+              (!w.stage_bytes || p.stage);
     if (!p.valid) return fail(ctx, LATER_B200_ENOMEM, "workspace carve failed");
     return 0;
 }
@@ -364,7 +413,7 @@ int prepare_plan(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R,
 // Enqueues one factorisation on ctx->stream (directly, or into an ongoing capture): the plain
 // launch sequence for a device matrix, or the same with the PCIe copies of the host entry point
 // forked around it.
-enum Stage : int { STAGE_ALL = 0, STAGE_HOST = 1 };
+enum Stage : int { STAGE_ALL = 0, STAGE_HOST = 1, STAGE_DIST = 2 };
 
 int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
     auto& p = ctx->plan;
@@ -408,7 +457,7 @@ int enqueue_stage(later_b200_ctx* ctx, int stage, long* launches) {
 
 bool same_plan(const later_b200_ctx::Plan& a, const later_b200_ctx::Plan& b) {
     return a.valid && b.valid && a.m == b.m && a.n == b.n && a.A == b.A && a.lda == b.lda &&
-           a.R == b.R && a.ldr == b.ldr && a.Qh == b.Qh && a.arena_gen == b.arena_gen &&
+           a.R == b.R && a.ldr == b.ldr && a.Qh == b.Qh && a.arena_gen == b.arena_gen && a.dist == b.dist &&
            a.hA == b.hA && a.hlda == b.hlda && a.hR == b.hR && a.hldr == b.hldr;
 }
 
@@ -484,10 +533,10 @@ int run_stage(later_b200_ctx* ctx, int stage) {
     return 0;
 }
 
-int rgsqrf_prepare(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
+int rgsqrf_prepare(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr, bool dist = false) {
     int rc = validate(ctx, m, n, A, lda, R, ldr);
     if (rc) return rc;
-    return prepare_plan(ctx, m, n, A, lda, R, ldr);
+    return prepare_plan(ctx, m, n, A, lda, R, ldr, dist);
 }
 
 int rgsqrf_device(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
@@ -594,6 +643,7 @@ int later_b200_destroy(later_b200_ctx* ctx) {
     if (ctx->dA) cudaFree(ctx->dA);
     if (ctx->dR) cudaFree(ctx->dR);
     if (ctx->aux) cudaFree(ctx->aux);
+    if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     ctx->arena.release();
@@ -640,6 +690,73 @@ int later_b200_graph_stats(const later_b200_ctx* ctx, long* replays, long* captu
 
 int later_b200_rgsqrf(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* R, int ldr) {
     return rgsqrf_device(ctx, m, n, A, lda, R, ldr);
+}
+
+// ---- row-sharded factorisation: the same recursion on this rank's row block, with the Gram matrix of
+// every panel and every R12 block summed over the ranks (NCCL all-reduce), so that all ranks factor the
+// GLOBAL matrix: same algorithm, same accuracy as one GPU, 1/P of the work each, no redundant stack
+// factorisation and no back-multiplication.
+int later_b200_comm_unique_id(void* id128) {
+    if (!id128) return LATER_B200_EINVAL;
+    std::string err;
+    Nccl* nccl = Nccl::get(&err);
+    if (!nccl) { fprintf(stderr, "later_b200: %s\n", err.c_str()); return LATER_B200_ESTATE; }
+    NcclUniqueId id;
+    if (nccl->GetUniqueId(&id) != 0) return LATER_B200_ESTATE;
+    memcpy(id128, id.internal, kNcclUniqueIdBytes);
+    return 0;
+}
+
+int later_b200_comm_init(later_b200_ctx* ctx, int nranks, int rank, const void* id128) {
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return LATER_B200_EINVAL;
+    if (ctx->comm) return fail(ctx, LATER_B200_ESTATE, "context already has a communicator");
+    std::string err;
+    ctx->nccl = Nccl::get(&err);
+    if (!ctx->nccl) return fail(ctx, LATER_B200_ESTATE, err);
+    DeviceGuard guard(ctx->device);
+    NcclUniqueId id;
+    memcpy(id.internal, id128, kNcclUniqueIdBytes);
+    const ncclResult_t r = ctx->nccl->CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != 0) {
+        ctx->comm = nullptr;
+        return fail(ctx, LATER_B200_ESTATE, std::string("ncclCommInitRank: ") + ctx->nccl->GetErrorString(r));
+    }
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return 0;
+}
+
+int later_b200_comm_init_all(later_b200_ctx* const* ctxs, int nranks) {
+    if (!ctxs || nranks < 1) return LATER_B200_EINVAL;
+    std::string err;
+    Nccl* nccl = Nccl::get(&err);
+    std::vector<int> devices(nranks);
+    for (int p = 0; p < nranks; ++p) {
+        if (!ctxs[p]) return LATER_B200_EINVAL;
+        if (!nccl) return fail(ctxs[p], LATER_B200_ESTATE, err);
+        if (ctxs[p]->comm) return fail(ctxs[p], LATER_B200_ESTATE, "context already has a communicator");
+        devices[p] = ctxs[p]->device;
+    }
+    std::vector<ncclComm_t> comms(nranks, nullptr);
+    const ncclResult_t r = nccl->CommInitAll(comms.data(), nranks, devices.data());
+    if (r != 0) return fail(ctxs[0], LATER_B200_ESTATE, std::string("ncclCommInitAll: ") + nccl->GetErrorString(r));
+    for (int p = 0; p < nranks; ++p) {
+        ctxs[p]->nccl = nccl;
+        ctxs[p]->comm = comms[p];
+        ctxs[p]->nranks = nranks;
+        ctxs[p]->rank = p;
+    }
+    return 0;
+}
+
+int later_b200_rgsqrf_dist(later_b200_ctx* ctx, int m_local, int n, float* A, int lda, float* R, int ldr) {
+    if (!ctx) return LATER_B200_EINVAL;
+    if (!ctx->comm) return fail(ctx, LATER_B200_ESTATE, "later_b200_rgsqrf_dist needs later_b200_comm_init first");
+    DeviceGuard guard(ctx->device);
+    if (guard.error() != cudaSuccess) return cuda_fail(ctx, guard.error(), "cudaSetDevice");
+    int rc = rgsqrf_prepare(ctx, m_local, n, A, lda, R, ldr, true);
+    if (rc) return rc;
+    return run_stage(ctx, STAGE_DIST);
 }
 
 // Gram-Schmidt twice ("CGS2-style" re-orthogonalisation): A = Q1 R1, Q1 = Q2 R2,

@@ -152,6 +152,35 @@ def later_qdwh_polar(ctxt: Context | None, n: int, A: torch.Tensor, lda: int, H,
     return int(it.value)
 
 
+def comm_init(ctxt: Context, group=None) -> None:
+    """Gives the context an NCCL communicator over the ranks of a torch.distributed group (one rank per
+    GPU): rank 0 draws the NCCL unique id, torch.distributed carries its 128 bytes to the others."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        rc = lib.later_b200_comm_unique_id(buf)
+        if rc != 0:
+            raise LaterError(rc, "later_b200_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=f"cuda:{ctxt.device}")
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    raw = bytes(t.cpu().tolist())
+    rc = lib.later_b200_comm_init(ctxt._h, world, rank, raw)
+    if rc != 0:
+        ctxt._raise(rc)
+
+
+def later_rgsqrf_dist(ctxt: Context, m_local: int, n: int, A: torch.Tensor, lda: int, R: torch.Tensor,
+                      ldr: int) -> None:
+    """Row-sharded RGSQRF (collective over the ranks of comm_init): A (this rank's m_local x n row block)
+    <- its rows of the global Q, R <- the global R, identical on every rank (include/later_b200.h)."""
+    _check_colmajor("A", A, m_local, n, lda)
+    _check_colmajor("R", R, n, n, ldr)
+    rc = lib.later_b200_rgsqrf_dist(ctxt._h, m_local, n, A.data_ptr(), lda, R.data_ptr(), ldr)
+    if rc != 0:
+        ctxt._raise(rc)
+
+
 def later_rgsqrf_host(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int,
                       R: torch.Tensor, ldr: int) -> None:
     """Same with HOST (ideally pinned) buffers; H2D and D2H copies happen inside the call, overlapped

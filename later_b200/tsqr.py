@@ -83,3 +83,58 @@ def tsqr_rgsqrf(m_local: int, n: int, A: torch.Tensor, lda: int, R: torch.Tensor
     W = S[rank * n:(rank + 1) * n, :]                                    # column-major view, ld = P*n
     apply_w(m_local, n, A, lda, W, world * n)
     R[:n, :n].copy_(Rs)
+
+
+class MultiGpu:
+    """Single-process driver of the same algorithm through the C ABI (later_b200_tsqr_mgpu): one host
+    thread, P devices, one NCCL all-gather of the local R factors.  A[p], R[p] live on device p."""
+
+    def __init__(self, devices):
+        import ctypes as C
+        from ._lib import lib
+        self._lib, self._C = lib, C
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        rc = lib.later_b200_mgpu_create(C.byref(h), len(self.devices), arr)
+        if rc != 0:
+            raise RuntimeError(f"later_b200_mgpu_create failed: {rc}")
+        self._h = h
+
+    def tsqr(self, m_local: int, n: int, A: list, lda: int, R: list, ldr: int) -> None:
+        C = self._C
+        P = len(self.devices)
+        pa = (C.c_void_p * P)(*[a.data_ptr() for a in A])
+        pr = (C.c_void_p * P)(*[r.data_ptr() for r in R])
+        rc = self._lib.later_b200_tsqr_mgpu(self._h, m_local, n, pa, lda, pr, ldr)
+        if rc != 0:
+            raise RuntimeError(f"later_b200_tsqr_mgpu: {rc}: "
+                               f"{self._lib.later_b200_mgpu_last_error(self._h).decode(errors='replace')}")
+
+    def rgsqrf(self, m_local: int, n: int, A: list, lda: int, R: list, ldr: int) -> None:
+        """The row-sharded recursion (later_b200_rgsqrf_mgpu): preferred - single-GPU accuracy, no
+        redundant stack factorisation, no back-multiplication."""
+        C = self._C
+        P = len(self.devices)
+        pa = (C.c_void_p * P)(*[a.data_ptr() for a in A])
+        pr = (C.c_void_p * P)(*[r.data_ptr() for r in R])
+        rc = self._lib.later_b200_rgsqrf_mgpu(self._h, m_local, n, pa, lda, pr, ldr)
+        if rc != 0:
+            raise RuntimeError(f"later_b200_rgsqrf_mgpu: {rc}: "
+                               f"{self._lib.later_b200_mgpu_last_error(self._h).decode(errors='replace')}")
+
+    def sync(self) -> None:
+        rc = self._lib.later_b200_mgpu_sync(self._h)
+        if rc != 0:
+            raise RuntimeError(f"later_b200_mgpu_sync: {rc}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.later_b200_mgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -52,6 +52,34 @@ def main():
         tsqr_rgsqrf(mloc, n, A2, mloc, R2, n, ctxs=ctxs, host_A=hA.t())
         torch.cuda.synchronize()
         ok = ok and torch.equal(A2, A) and torch.equal(R2, R)
+    # the row-sharded recursion (all-reduces inside): single-GPU accuracy, identical R on every rank,
+    # direct / capturing / replaying call bit-identical
+    # (own non-blocking stream: the library's NCCL collectives must not sit on the legacy default stream,
+    # which synchronises implicitly with every blocking stream of the process)
+    side = torch.cuda.Stream()
+    dctx = qr.Context(stream=side)
+    qr.comm_init(dctx)
+    A3 = qr.colmajor_empty(mloc, n)
+    R3 = qr.colmajor_empty(n, n)
+    outs = []
+    for _ in range(3):
+        A3.copy_(A0)
+        R3.fill_(float("nan"))
+        side.wait_stream(torch.cuda.current_stream())
+        qr.later_rgsqrf_dist(dctx, mloc, n, A3, mloc, R3, n)
+        side.synchronize()
+        outs.append((A3.clone(), R3.clone()))
+    ok = ok and all(torch.equal(outs[0][0], a) and torch.equal(outs[0][1], r) for a, r in outs[1:])
+    Rs3 = [torch.empty_like(R3.contiguous()) for _ in range(world)]
+    dist.all_gather(Rs3, R3.contiguous())
+    same3 = all(torch.equal(Rs3[0], x) for x in Rs3)
+    res3 = torch.linalg.norm((A0 - A3 @ R3).double()) ** 2
+    G3 = (A3.t() @ A3).double()
+    dist.all_reduce(res3); dist.all_reduce(G3)
+    back3 = float(torch.sqrt(res3 / nrm2))
+    G3.diagonal().sub_(1.0)
+    orth3 = float(torch.linalg.norm(G3) / n)
+    ok = ok and same3 and bool((R3.diagonal() > 0).all()) and float(torch.tril(R3, -1).abs().max()) == 0.0
     if rank == 0:
         # against the single-GPU factorisation of the whole matrix
         c = qr.Context()
@@ -60,6 +88,15 @@ def main():
         qr.later_rgsqrf(c, m, n, A1, m, R1, n)
         rdiff = float((R - R1).abs().max() / R1.abs().max())
         ok = ok and rdiff < 5e-3
+        # the row-sharded recursion must be as accurate as the single-GPU factorisation (within 2x)
+        back1 = float(torch.linalg.norm((A_glob - A1 @ R1).double()) / torch.linalg.norm(A_glob.double()))
+        G1 = (A1.t() @ A1).double()
+        G1.diagonal().sub_(1.0)
+        orth1 = float(torch.linalg.norm(G1) / n)
+        rdiff3 = float((R3 - R1).abs().max() / R1.abs().max())
+        ok = ok and back3 <= 2 * back1 + 1e-7 and orth3 <= 2 * orth1 + 1e-8 and rdiff3 < 5e-3
+        print(f"DIST world={world} {m}x{n}: same_R={same3} backward={back3:.3e} (1 GPU {back1:.3e}) "
+              f"orth/n={orth3:.3e} (1 GPU {orth1:.3e}) |R-R1|/|R1|={rdiff3:.3e}", flush=True)
         print(f"TSQR world={world} {m}x{n}: same_R={same} backward={back:.3e} orth/n={orth:.3e} "
               f"|R-R1|/|R1|={rdiff:.3e} {'OK' if ok else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
