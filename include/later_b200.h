@@ -81,6 +81,17 @@ int later_b200_qdwh_polar(later_b200_ctx* ctx, int n, float* X, int ldx, float* 
 int later_b200_rgsqrf_host(later_b200_ctx* ctx, int m, int n, float* hA, int lda, float* hR,
                            int ldr);
 
+/* Out-of-core front end (reference later_oc_qr_rec / later_oc_qr_blk, QR/later_oc_qr.cu:29-121): the
+ * host matrix may be larger than device memory.  Column blocks of block_cols (128 * 2^k, a divisor of
+ * n; the reference's BLOCKSIZE is 8192) stream through a device window of three blocks: every block
+ * receives the projections of all finished blocks (R_ij = Q_i^T A_j, A_j -= Q_i R_ij, the finished Q_i
+ * re-read from the host, double-buffered), is factored in core and leaves.  hA <- Q; hR <- the block
+ * upper triangle at that granularity (blocks below are not written, as with later_b200_rgsqrf_host).
+ * Device memory: 12 m block_cols bytes + the workspace of an m x 3 block_cols factorisation.  Blocks until
+ * done; returns LATER_B200_ERANK like later_b200_rgsqrf_host.  info[0] of later_b200_last_info counts columns
+ * inside the block being factored. */
+int later_b200_oc_qr(later_b200_ctx* ctx, int m, int n, float* hA, int lda, float* hR, int ldr, int block_cols);
+
 /* Host in, device out: the columns of hA (host, ideally page-locked) are copied into A (device) and
  * factored as they arrive, exactly as in later_b200_rgsqrf_host, but Q (in A) and R stay on the
  * device and the call is asynchronous on the context's stream like later_b200_rgsqrf.  This is the

@@ -24,6 +24,7 @@ SYMBOLS = {
     "later_b200_qdwh_polar": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float,
                                         C.c_int, C.POINTER(C.c_int)]),
     "later_b200_rgsqrf_host": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "later_b200_oc_qr": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "later_b200_rgsqrf_stream_in": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                               C.c_void_p, C.c_int]),
     "later_b200_panel_qr": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

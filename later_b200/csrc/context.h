@@ -83,6 +83,7 @@ struct later_b200_ctx {
     lb::Nccl* nccl = nullptr;
     lb::ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    std::shared_ptr<lb::CommGroup> comm_group;   // set when the ranks are contexts of this process
     // scratch of the callers built on top of the factorisation (re-orthogonalisation, QDWH): lives
     // outside the arena, which every factorisation carves anew
     void* aux = nullptr; size_t aux_bytes = 0;
@@ -103,7 +104,9 @@ class DeviceGuard {
 public:
     explicit DeviceGuard(int device) {
         if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
-        err_ = prev_ == device ? cudaSuccess : cudaSetDevice(device);
+        // (always: in a thread that has made no runtime call yet, cudaGetDevice reports device 0 without
+        // binding its context, and the driver-API tensor-map encoder then fails with "invalid argument")
+        err_ = cudaSetDevice(device);
         if (prev_ == device) prev_ = -1;          // nothing to restore
     }
     ~DeviceGuard() { if (prev_ >= 0) cudaSetDevice(prev_); }

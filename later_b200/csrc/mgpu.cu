@@ -190,10 +190,11 @@ int later_b200_rgsqrf_mgpu(later_b200_mgpu* g, int m_local, int n, float* const*
         int rc = later_b200_rgsqrf(g->main_ctx[0], m_local, n, A[0], lda, R[0], ldr);
         return rc ? mfail(g, rc, later_b200_last_error(g->main_ctx[0])) : 0;
     }
-    // one host thread per device: each enqueues (or captures / replays) its own launch sequence, whose
-    // all-reduces meet the other devices' on the GPUs
+    // one host thread per device, each enqueuing its own launch sequence; at every all-reduce the threads
+    // meet and ONE of them issues the P requests inside one NCCL group call (lb::CommGroup)
     std::vector<int> rcs(P, 0);
     std::vector<std::thread> threads;
+    if (g->main_ctx[0]->comm_group) g->main_ctx[0]->comm_group->reset();
     for (int p = 0; p < P; ++p)
         threads.emplace_back([&, p] { rcs[p] = later_b200_rgsqrf_dist(g->main_ctx[p], m_local, n, A[p], lda, R[p], ldr); });
     for (auto& t : threads) t.join();

@@ -5,7 +5,9 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <condition_variable>
 #include <cstddef>
+#include <memory>
 #include <mutex>
 #include <string>
 
@@ -61,6 +63,52 @@ private:
         GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
         GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
         GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+    }
+};
+
+// The P contexts of ONE process that share a communicator set (later_b200_comm_init_all): NCCL wants the
+// collectives of several devices driven from one process to be issued together, inside one group call
+// by one thread.  Every context's host thread brings its request here; the last one to arrive issues
+// all P of them and releases the others.
+struct CommGroup {
+    static constexpr int kMax = 16;
+    std::mutex mu;
+    std::condition_variable cv;
+    int P = 0, arrived = 0;
+    long generation = 0;
+    bool failed = false;
+    struct Req { void* buf; size_t count; int dtype; cudaStream_t stream; ncclComm_t comm; } req[kMax];
+
+    // returns 0, an NCCL error code, or -1 when another rank gave up
+    int allreduce(Nccl* nccl, int rank, void* buf, size_t count, int dtype, ncclComm_t comm, cudaStream_t stream) {
+        std::unique_lock<std::mutex> lock(mu);
+        if (failed) return -1;
+        req[rank] = Req{buf, count, dtype, stream, comm};
+        if (++arrived == P) {
+            ncclResult_t r = nccl->GroupStart();
+            for (int p = 0; p < P && r == 0; ++p)
+                r = nccl->AllReduce(req[p].buf, req[p].buf, req[p].count, req[p].dtype, kNcclSum, req[p].comm, req[p].stream);
+            const ncclResult_t r2 = nccl->GroupEnd();
+            if (r == 0) r = r2;
+            arrived = 0;
+            ++generation;
+            if (r != 0) failed = true;
+            cv.notify_all();
+            return r;
+        }
+        const long gen = generation;
+        cv.wait(lock, [&] { return generation != gen || failed; });
+        return failed ? -1 : 0;
+    }
+    void abort() {
+        std::lock_guard<std::mutex> lock(mu);
+        failed = true;
+        cv.notify_all();
+    }
+    void reset() {
+        std::lock_guard<std::mutex> lock(mu);
+        failed = false;
+        arrived = 0;
     }
 };
 

@@ -214,9 +214,12 @@ __global__ void finish_r12_kernel(const float* __restrict__ S, int h, int nb, fl
 
 cudaError_t comm_allreduce(later_b200_ctx* ctx, void* buf, size_t count, int dtype, cudaStream_t stream) {
     if (!ctx->comm || !ctx->nccl) return cudaErrorNotReady;
-    const ncclResult_t r = ctx->nccl->AllReduce(buf, buf, count, dtype, kNcclSum, ctx->comm, stream);
+    const ncclResult_t r = ctx->comm_group
+        ? ctx->comm_group->allreduce(ctx->nccl, ctx->rank, buf, count, dtype, ctx->comm, stream)
+        : ctx->nccl->AllReduce(buf, buf, count, dtype, kNcclSum, ctx->comm, stream);
     if (r != 0) {
-        ctx->error = std::string("ncclAllReduce: ") + ctx->nccl->GetErrorString(r);
+        ctx->error = r < 0 ? std::string("another rank of this process gave up")
+                           : std::string("ncclAllReduce: ") + ctx->nccl->GetErrorString(r);
         return cudaErrorUnknown;
     }
     return cudaSuccess;
@@ -313,11 +316,10 @@ struct Recursion {
         if (update_uses_tma(h) && p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
             // columns cb .. cb + 127 are the next panel: if it will use the integer Gram kernel, this
             // update leaves their maxima behind and saves that kernel its first pass over the panel
-            // (worth its ~2 % of epilogue work only when that pass would come from HBM: a panel that
-            // still sits in the 126 MB L2 after this update is scanned in ~10 us)
+            // (~2 % more epilogue work against a separate launch that costs 15 us even when the panel
+            // still sits in L2: 5 % of the step on a 131072-row shard)
             const bool want = panel_uses_i8_gram(p->m, ctx->num_sms, p->A + (long)cb * p->lda, p->lda, true,
-                                                 ctx->opts.panel) &&
-                              (size_t)p->m * kPanelWidth * sizeof(float) > ((size_t)96 << 20);
+                                                 ctx->opts.panel);
             check(tc_update_tma(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, nb, p->A, p->m,
                                 p->n, p->lda, cb, p->Qh, p->ldh, true,
                                 want ? panel_colmax_scratch(p->panel_scratch, p->m, ctx->num_sms) : nullptr,
@@ -740,11 +742,15 @@ int later_b200_comm_init_all(later_b200_ctx* const* ctxs, int nranks) {
     std::vector<ncclComm_t> comms(nranks, nullptr);
     const ncclResult_t r = nccl->CommInitAll(comms.data(), nranks, devices.data());
     if (r != 0) return fail(ctxs[0], LATER_B200_ESTATE, std::string("ncclCommInitAll: ") + nccl->GetErrorString(r));
+    if (nranks > CommGroup::kMax) return fail(ctxs[0], LATER_B200_EINVAL, "too many ranks in one process");
+    auto group = std::make_shared<CommGroup>();
+    group->P = nranks;
     for (int p = 0; p < nranks; ++p) {
         ctxs[p]->nccl = nccl;
         ctxs[p]->comm = comms[p];
         ctxs[p]->nranks = nranks;
         ctxs[p]->rank = p;
+        ctxs[p]->comm_group = group;
     }
     return 0;
 }
@@ -755,8 +761,17 @@ int later_b200_rgsqrf_dist(later_b200_ctx* ctx, int m_local, int n, float* A, in
     DeviceGuard guard(ctx->device);
     if (guard.error() != cudaSuccess) return cuda_fail(ctx, guard.error(), "cudaSetDevice");
     int rc = rgsqrf_prepare(ctx, m_local, n, A, lda, R, ldr, true);
-    if (rc) return rc;
-    return run_stage(ctx, STAGE_DIST);
+    if (rc == 0) {
+        // (ranks that are threads of this process meet inside every all-reduce: plain stream launches
+        // then - capturing NCCL operations of several devices into separate graphs concurrently is not
+        // something to rely on; the one-process-per-GPU form replays graphs)
+        const bool graph = ctx->use_graph;
+        if (ctx->comm_group) ctx->use_graph = false;
+        rc = run_stage(ctx, STAGE_DIST);
+        ctx->use_graph = graph;
+    }
+    if (rc && ctx->comm_group) ctx->comm_group->abort();     // do not leave the other threads waiting
+    return rc;
 }
 
 // Gram-Schmidt twice ("CGS2-style" re-orthogonalisation): A = Q1 R1, Q1 = Q2 R2,
@@ -787,6 +802,123 @@ int later_b200_rgsqrf_reorth(later_b200_ctx* ctx, int m, int n, float* A, int ld
     rc = split_gemm_nn(ctx, n, n, n, R2, n, R1, n, R, ldr, scratch, &launches);
     ctx->launches = launches;
     return rc;
+}
+
+// Out-of-core front end (reference QR/later_oc_qr.cu:29-121): the matrix lives in host
+// memory and may be larger than the device.  Column blocks of width B stream through a device window of
+// three blocks - two slots for finished Q blocks arriving from the host, one for the block being worked on:
+//   for block j:  A_j -> device;  for i < j:  Q_i -> device (next slot, while the previous product runs),
+//                 R_ij = Q_i^T A_j,  A_j -= Q_i R_ij   (the tcgen05 trailing-update pair);
+//                 A_j = Q_j R_jj (the in-core recursion);  Q_j, R_ij, R_jj -> host.
+// Block Gram-Schmidt with sequential projections, as the reference's recursion does between its
+// 8192-column panels (QR/later_oc_qr.cu:70-88), on the same kernels as the in-core path.
+int later_b200_oc_qr(later_b200_ctx* ctx, int m, int n, float* hA, int lda, float* hR, int ldr, int block_cols) {
+    if (!ctx) return LATER_B200_EINVAL;
+    if (!hA || !hR) return fail(ctx, LATER_B200_EINVAL, "null matrix pointer");
+    const int B = block_cols;
+    if (B < NMIN || B % NMIN != 0 || ((B / NMIN) & (B / NMIN - 1)) != 0)
+        return fail(ctx, LATER_B200_EINVAL, "block_cols must be 128 * 2^k");
+    if (n < B || n % B != 0) return fail(ctx, LATER_B200_EINVAL, "n must be a multiple of block_cols");
+    if (m < n || m % 8 != 0) return fail(ctx, LATER_B200_EINVAL, "m must be >= n and a multiple of 8");
+    if (lda < m || ldr < n) return fail(ctx, LATER_B200_EINVAL, "leading dimension too small");
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = guard.error();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    if (!ctx->s_in) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(ctx, e, "copy streams");
+    }
+    // device window: m x 3B fp32 + its 3B x 3B R
+    const int W = 3 * B;
+    const size_t a_bytes = (size_t)m * W * sizeof(float), r_bytes = (size_t)W * W * sizeof(float);
+    if (ctx->dA_bytes < a_bytes) {
+        if (ctx->dA) cudaFree(ctx->dA);
+        ctx->dA = nullptr; ctx->dA_bytes = 0;
+        if ((e = cudaMalloc(&ctx->dA, a_bytes)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc window");
+        ctx->dA_bytes = a_bytes;
+    }
+    if (ctx->dR_bytes < r_bytes) {
+        if (ctx->dR) cudaFree(ctx->dR);
+        ctx->dR = nullptr; ctx->dR_bytes = 0;
+        if ((e = cudaMalloc(&ctx->dR, r_bytes)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc R");
+        ctx->dR_bytes = r_bytes;
+    }
+    float* D = ctx->dA;
+    float* Rw = ctx->dR;
+    int rc = prepare_plan(ctx, m, W, D, m, Rw, W);
+    if (rc) return rc;
+    auto& p = ctx->plan;
+    Recursion rec{};
+    rec.ctx = ctx;
+    rec.p = &p;
+    HalfMatrix qm{p.Qh, p.m, p.n, p.ldh};
+    if ((e = make_tensor_map_f16(&rec.q128, qm, 64, 128)) != cudaSuccess ||
+        (e = make_tensor_map_f16(&rec.q256, qm, 64, 256)) != cudaSuccess ||
+        (e = make_tensor_map_f16(&rec.q64, qm, 64, 64)) != cudaSuccess)
+        return cuda_fail(ctx, e, "tensor map encode");
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_r = nullptr;
+    for (auto* ev : {&ev_in[0], &ev_in[1], &ev_free[0], &ev_free[1], &ev_r})
+        if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(ctx, e, "event");
+    auto cleanup = [&]() { for (cudaEvent_t ev : {ev_in[0], ev_in[1], ev_free[0], ev_free[1], ev_r}) if (ev) cudaEventDestroy(ev); };
+    const size_t col = (size_t)m * sizeof(float);
+    auto h2d_block = [&](int slot, int jb, cudaStream_t s) {
+        return cudaMemcpy2DAsync(D + (size_t)slot * B * m, col, hA + (size_t)jb * B * lda, (size_t)lda * sizeof(float), col, B,
+                                 cudaMemcpyHostToDevice, s);
+    };
+    if ((e = cudaMemsetAsync(ctx->d_info, 0, kInfoWords * sizeof(int), st)) != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "info clear"); }
+    const int nb = n / B;
+    cudaError_t err = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (err == cudaSuccess && x != cudaSuccess) err = x; };
+    for (int j = 0; j < nb && err == cudaSuccess && rec.err == cudaSuccess; ++j) {
+        ck(h2d_block(2, j, st));                                     // the block to work on
+        if (j > 0) {                                                 // first finished block on its way
+            // (the copy stream re-reads finished Q blocks from the host: it must stay behind the main
+            // stream's copy-out of the newest of them)
+            ck(cudaEventRecord(ev_r, st));
+            ck(cudaStreamWaitEvent(ctx->s_in, ev_r, 0));
+            ck(cudaStreamWaitEvent(ctx->s_in, ev_free[0], 0));
+            ck(h2d_block(0, 0, ctx->s_in));
+            ck(cudaEventRecord(ev_in[0], ctx->s_in));
+        }
+        for (int i = 0; i < j && err == cudaSuccess; ++i) {
+            const int slot = i & 1;
+            if (i + 1 < j) {                                         // prefetch the next Q block into the other slot
+                ck(cudaStreamWaitEvent(ctx->s_in, ev_free[slot ^ 1], 0));
+                ck(h2d_block(slot ^ 1, i + 1, ctx->s_in));
+                ck(cudaEventRecord(ev_in[slot ^ 1], ctx->s_in));
+            }
+            ck(cudaStreamWaitEvent(st, ev_in[slot], 0));
+            rec.cast(slot * B, slot * B + B);                        // fp16 operand of the two products
+            rec.gram_update(slot * B, B, 2 * B, B, false, i == 0);   // R_ij, A_j -= Q_i R_ij
+            ck(cudaEventRecord(ev_free[slot], st));
+            // R_ij -> host (ordered behind the products on the main stream; B x B, small)
+            ck(cudaMemcpy2DAsync(hR + (size_t)i * B + (size_t)j * B * ldr, (size_t)ldr * sizeof(float),
+                                 Rw + (size_t)slot * B + (size_t)2 * B * W, (size_t)W * sizeof(float), (size_t)B * sizeof(float), B,
+                                 cudaMemcpyDeviceToHost, st));
+        }
+        if (j == 0) rec.cast(2 * B, 3 * B);                          // (later blocks: the updates refreshed the shadow)
+        rec.qr(2 * B, B);
+        ck(cudaMemcpy2DAsync(hR + (size_t)j * B + (size_t)j * B * ldr, (size_t)ldr * sizeof(float),
+                             Rw + (size_t)2 * B + (size_t)2 * B * W, (size_t)W * sizeof(float), (size_t)B * sizeof(float), B,
+                             cudaMemcpyDeviceToHost, st));
+        ck(cudaMemcpy2DAsync(hA + (size_t)j * B * lda, (size_t)lda * sizeof(float), D + (size_t)2 * B * m, col, col, B,
+                             cudaMemcpyDeviceToHost, st));
+        if (j == 0) { ck(cudaEventRecord(ev_free[0], st)); ck(cudaEventRecord(ev_free[1], st)); }
+    }
+    if (err == cudaSuccess && rec.err == cudaSuccess)
+        ck(cudaMemcpyAsync(ctx->h_info, ctx->d_info, kInfoWords * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ck(cudaStreamSynchronize(ctx->s_in));
+    ck(cudaStreamSynchronize(st));
+    cleanup();
+    ctx->plan.valid = false;
+    ctx->launches = rec.launches;
+    if (rec.err != cudaSuccess) return cuda_fail(ctx, rec.err, "oc_qr enqueue");
+    if (err != cudaSuccess) return cuda_fail(ctx, err, "oc_qr");
+    if (ctx->h_info[INFO_BAD_COLUMN] != 0 || (ctx->h_info[INFO_FLAGS] & 1))
+        return fail(ctx, LATER_B200_ERANK, rank_message(ctx->h_info));
+    return 0;
 }
 
 // Shared by the two host-input entry points: factor the device matrix (dA, dR) while its columns

@@ -196,6 +196,20 @@ def later_rgsqrf_host(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda
         ctxt._raise(rc)
 
 
+def later_oc_qr(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int, R: torch.Tensor, ldr: int,
+                block_cols: int = 8192) -> None:
+    """Out-of-core QR of a HOST matrix (reference later_oc_qr_rec / _blk, QR/later_oc_qr.cu:29-121):
+    column blocks of block_cols stream through the device; A <- Q, R <- block upper triangle."""
+    ctxt = ctxt or default_context()
+    if A.is_cuda or R.is_cuda:
+        raise ValueError("later_oc_qr takes host tensors")
+    _check_colmajor("A", A, m, n, lda)
+    _check_colmajor("R", R, n, n, ldr)
+    rc = lib.later_b200_oc_qr(ctxt._h, m, n, A.data_ptr(), lda, R.data_ptr(), ldr, block_cols)
+    if rc != 0:
+        ctxt._raise(rc)
+
+
 def later_rgsqrf_stream_in(ctxt: Context | None, m: int, n: int, hA: torch.Tensor, hlda: int,
                            A: torch.Tensor, lda: int, R: torch.Tensor, ldr: int) -> None:
     """Host in, device out: hA (host, ideally pinned) is copied into A (device) column piece by

@@ -21,6 +21,7 @@ int main(int argc, char** argv) {
     const int m_local = argc > 2 ? atoi(argv[2]) : 16384;
     const int n = argc > 3 ? atoi(argv[3]) : 256;
     const bool use_tsqr = argc > 4 && strcmp(argv[4], "tsqr") == 0;      // default: the row-sharded recursion
+    setvbuf(stdout, nullptr, _IONBF, 0);
     int count = 0;
     CK(cudaGetDeviceCount(&count));
     if (count < P) { printf("SKIP: %d device(s), need %d\n", count, P); return 77; }

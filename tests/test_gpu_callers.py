@@ -162,3 +162,35 @@ def test_reorth_restores_orthogonality(qr, ctx, m, n, kappa):
     assert torch.tril(R2, -1).abs().max().item() == 0.0
     assert orth2 <= 5e-5 and orth2 <= 0.05 * orth1, (orth1, orth2)
     assert back2 <= 2 * back1 + 1e-6, (back1, back2)
+
+
+# ------------------------------------------------------------------------------ out-of-core front end
+@pytest.mark.parametrize("m,n,B,pinned", [(4096, 1024, 256, True), (2048, 512, 128, False), (8192, 2048, 1024, True),
+                                          (65544, 512, 128, True)])
+def test_out_of_core_qr_matches_the_in_core_factorisation(qr, ctx, m, n, B, pinned):
+    """later_oc_qr (reference QR/later_oc_qr.cu:29-121): host matrix, column blocks streamed through a
+    three-block device window.  Same factorisation as the in-core path up to the order of the
+    projections: metrics within 2x, R equal at fp16 level times conditioning, block upper triangle only."""
+    rng = np.random.default_rng(50)
+    A0 = rng.standard_normal((m, n), dtype=np.float32)
+    Ad = qr.to_colmajor(torch.from_numpy(A0).cuda())
+    Rd = qr.colmajor_empty(n, n)
+    qr.later_rgsqrf(ctx, m, n, Ad, m, Rd, n)
+    back_in, orth_in = metrics(torch.from_numpy(A0).cuda(), Ad, Rd)
+    bufA, bufR = torch.empty((n, m), dtype=torch.float32), torch.empty((n, n), dtype=torch.float32)
+    if pinned:
+        bufA, bufR = bufA.pin_memory(), bufR.pin_memory()
+    hA, hR = bufA.t(), bufR.t()
+    hA.copy_(torch.from_numpy(A0))
+    bufR.fill_(7.0)
+    qr.later_oc_qr(ctx, m, n, hA, m, hR, n, block_cols=B)
+    blk = np.arange(n) // B
+    mask = blk[:, None] <= blk[None, :]
+    got = hR.numpy()
+    assert np.all(got[~mask] == 7.0)                       # blocks below the diagonal are left alone
+    R = np.where(mask, got, 0.0).astype(np.float32)
+    assert np.abs(np.tril(R, -1)).max() == 0.0 and (np.diag(R) > 0).all()
+    back, orth = metrics(torch.from_numpy(A0).cuda(), hA.cuda(), torch.from_numpy(R).cuda())
+    assert back <= 2 * back_in + 1e-7 and orth <= 2 * orth_in + 1e-8, (back, back_in, orth, orth_in)
+    cond = np.linalg.cond(A0.astype(np.float64))
+    assert np.abs(R - Rd.cpu().numpy()).max() <= 2e-3 * cond * np.abs(R).max()
