@@ -40,8 +40,9 @@ void later_rgsqrf(cudaCtxt ctxt, int m, int n, float* A, int lda, float* R, int 
 void later_ormqr(int m, int n, float* W, int ldw, float* Y, int ldy, float* work);
 void later_ormqr2(int m, int n, float* W, int ldw, float* Y, int ldy, float* work);
 
-// Householder QR variants are OUT OF SCOPE of this library: these exist only so
-// the reference driver links; calling them prints a message and exits with status 2.
+// Recursive / blocked Householder QR in WY form (reference include/LATER.h:41,45; QR/later_rhouqr.cu,
+// QR/later_bhouqr.cu): A <- Y, W, R out; later_ormqr (after later_rhouqr) or later_ormqr2 (after
+// later_bhouqr) forms the explicit Q = I - W Y^T.  work, hwork and U are accepted and ignored.
 void later_rhouqr(cudaCtxt ctxt, int m, int n, float* A, int lda, float* W, int ldw, float* R,
                   int ldr, float* work, int lwork, __half* hwork, int lhwork, float* U);
 void later_bhouqr(int m, int n, float* A, int lda, float* W, int ldw, float* R, int ldr,

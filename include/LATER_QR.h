@@ -21,8 +21,7 @@ void mgs_caqr_panel_256x32(cudaCtxt ctxt, int m, int n, float* A, int lda, float
 __global__ void mgs_kernel(int m, int n, float* AA, int lda, float* RR, int ldr);
 __global__ void mgs_kernel2(int m, int n, float* AA, int lda, float* RR, int ldr);
 
-// Householder CAQR panel (reference QR/panel.cu:341-378): NOT part of the Gram-Schmidt path
-// (SURVEY.md par.8 f2).  Declared so that test/test_caqr_panel.cu links; the <256, 32> instance
-// reports that it is out of scope and returns without touching A or R.
+// Householder CAQR strip (reference QR/panel.cu:341-378): A (m x 32) <- explicit Q, R <- its factor.
+// Only the <256, 32> instance exists, as in the reference (QR/panel.cu:811).
 template <int M, int N>
 void hou_caqr_panel(cudaCtxt ctxt, int m, int n, float* A, int lda, float* R, int ldr, float* work);

@@ -154,6 +154,16 @@ int later_b200_rgsqrf_mgpu(later_b200_mgpu* g, int m_local, int n, float* const*
 int later_b200_mgpu_sync(later_b200_mgpu* g);
 const char* later_b200_mgpu_last_error(const later_b200_mgpu* g);
 
+/* Recursive Householder QR in WY form.  Replaces later_rhouqr (reference include/LATER.h:41,
+ * QR/later_rhouqr.cu:21-201) and, with merge_top = 1, later_bhouqr: A (device, m x n) <- Y (unit lower
+ * trapezoidal Householder vectors), W (device, m x n) <- the W factor of Q = I - W Y^T, R (n x n) <-
+ * upper triangular (its diagonal may be negative).  merge_top = 0 leaves the merge of the two halves of
+ * W at the top level to later_b200_ormqr, which performs it first (the reference's own driver calls
+ * later_rhouqr + later_ormqr, test/test_qr.cu:116-127); merge_top = 1 returns the complete W, for
+ * later_b200_ormqr2 (test/test_qr.cu:160-172).  n = 32 * 2^k, m >= n, m a multiple of 8. */
+int later_b200_rhouqr(later_b200_ctx* ctx, int m, int n, float* A, int lda, float* W, int ldw, float* R, int ldr,
+                      int merge_top);
+
 /* Explicit Q from a Householder WY pair.  Replaces later_ormqr (reference include/LATER.h:43,
  * QR/later_ormqr.cu:18-64): W[:, n/2:] -= W[:, :n/2] * (Y[:, :n/2]^T W[:, n/2:]), then
  * W <- I - W * Y[0:n, 0:n]^T.  fp32-faithful (split-precision tensor-core products). */

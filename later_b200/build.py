@@ -32,6 +32,7 @@ SOURCES = {
     "rgsqrf.cu": [],
     "ormqr.cu": [],
     "qdwh.cu": [],
+    "hou.cu": [],
     "mgpu.cu": [],
     "compat.cu": ["-rdc=true"],
 }

@@ -77,10 +77,12 @@ void mgs_caqr_panel_256x32(cudaCtxt, int m, int n, float* A, int lda, float* R, 
     die_on(later_b200_panel32_qr(default_ctx(), m, n, A, lda, R, ldr), "mgs_caqr_panel_256x32");
 }
 
+// Householder CAQR strip (reference QR/panel.cu:341-378): A <- explicit Q, R <- 32 x 32 factor.  Served by
+// the Gram/Cholesky strip factorisation (r_ii > 0; the reference's reflectors give r_ii < 0).
 template <int M, int N>
-void hou_caqr_panel(cudaCtxt, int, int, float*, int, float*, int, float*) {
-    fprintf(stderr, "hou_caqr_panel<%d,%d>: Householder CAQR is out of scope of later_b200 (RGSQRF path only); "
-                    "A and R are left untouched\n", M, N);
+void hou_caqr_panel(cudaCtxt, int m, int n, float* A, int lda, float* R, int ldr, float*) {
+    static_assert(N == 32, "only the 32-column strip exists");
+    die_on(later_b200_panel32_qr(default_ctx(), m, n, A, lda, R, ldr), "hou_caqr_panel");
 }
 template void hou_caqr_panel<256, 32>(cudaCtxt, int, int, float*, int, float*, int, float*);
 
@@ -98,16 +100,14 @@ void later_qdwh_polar(cudaCtxt, int n, float* A, int lda, float*, int, float* tm
     printf("later_qdwh_polar: %d iterations\n", iters);
 }
 
-void later_rhouqr(cudaCtxt, int, int, float*, int, float*, int, float*, int, float*, int, __half*,
+void later_rhouqr(cudaCtxt, int m, int n, float* A, int lda, float* W, int ldw, float* R, int ldr, float*, int, __half*,
                   int, float*) {
-    fprintf(stderr, "later_rhouqr: Householder QR is out of scope of later_b200 (RGSQRF path only)\n");
-    exit(2);
+    die_on(later_b200_rhouqr(default_ctx(), m, n, A, lda, W, ldw, R, ldr, 0), "later_rhouqr");
 }
 
-void later_bhouqr(int, int, float*, int, float*, int, float*, int, float*, int, __half*, int,
+void later_bhouqr(int m, int n, float* A, int lda, float* W, int ldw, float* R, int ldr, float*, int, __half*, int,
                   float*) {
-    fprintf(stderr, "later_bhouqr: Householder QR is out of scope of later_b200 (RGSQRF path only)\n");
-    exit(2);
+    die_on(later_b200_rhouqr(default_ctx(), m, n, A, lda, W, ldw, R, ldr, 1), "later_bhouqr");
 }
 
 void startTimer() {

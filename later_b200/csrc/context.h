@@ -99,6 +99,11 @@ size_t split_gemm_scratch_bytes(int M, int N, int K);
 int split_gemm_nn(later_b200_ctx* ctx, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
                   float* C, long ldc, void* scratch, long* launches);
 
+// C2 -= X (Z^T C2), fp32 column-major, `rows` rows (Z, X: rows x h; C2: rows x nb), fp32-faithful (ormqr.cu).
+size_t split_project_scratch_bytes(int rows, int h, int nb);
+int split_project(later_b200_ctx* ctx, int rows, int h, int nb, const float* Z, long ldz, const float* X, long ldx,
+                  float* C2, long ldc, void* scratch, long* launches);
+
 // Makes the context's device current for the duration of a C-ABI call and restores the caller's.
 class DeviceGuard {
 public:

@@ -279,6 +279,63 @@ int split_gemm_nn(later_b200_ctx* ctx, int M, int N, int K, const float* A, long
     return 0;
 }
 
+// C2 -= X (Z^T C2) with every matrix fp32 column-major and `rows` rows (Z, X: rows x h; C2: rows x nb),
+// fp32-faithful: the same two split-precision product triples as the merge step of later_ormqr.
+size_t split_project_scratch_bytes(int rows, int h, int nb) {
+    const size_t ldp = round_up(rows, 8);
+    return 4 * round_up(ldp * h * sizeof(__half), 256) + 2 * round_up(ldp * nb * sizeof(__half), 256) +
+           2 * round_up((size_t)round_up(h, 8) * nb * sizeof(__half), 256) + round_up((size_t)h * nb * sizeof(float), 256) +
+           1024;
+}
+
+int split_project(later_b200_ctx* ctx, int rows, int h, int nb, const float* Z, long ldz, const float* X, long ldx,
+                  float* C2, long ldc, void* scratch, long* launches) {
+    if (rows % 8 != 0) return fail(ctx, LATER_B200_EINVAL, "split_project: rows must be a multiple of 8");
+    uint8_t* base = static_cast<uint8_t*>(scratch);
+    const long ldp = round_up(rows, 8), ldk = round_up(h, 8);
+    const size_t pz = round_up((size_t)ldp * h * sizeof(__half), 256), pc = round_up((size_t)ldp * nb * sizeof(__half), 256);
+    const size_t pk = round_up((size_t)ldk * nb * sizeof(__half), 256);
+    Planes Zp{(__half*)base, (__half*)(base + pz), ldp};
+    Planes Xp{(__half*)(base + 2 * pz), (__half*)(base + 3 * pz), ldp};
+    Planes Cp{(__half*)(base + 4 * pz), (__half*)(base + 4 * pz + pc), ldp};
+    Planes Kp{(__half*)(base + 4 * pz + 2 * pc), (__half*)(base + 4 * pz + 2 * pc + pk), ldk};
+    float* work = reinterpret_cast<float*>(base + 4 * pz + 2 * pc + 2 * pk);
+    float* scal = reinterpret_cast<float*>(base + 4 * pz + 2 * pc + 2 * pk + round_up((size_t)h * nb * sizeof(float), 256));
+    Ormqr o{};
+    o.ctx = ctx; o.st = ctx->stream;
+    o.kChunk = ctx->opts.ormqr_kchunk;
+    o.slot = reinterpret_cast<unsigned*>(scal + 32);
+    o.sW = scal; o.sY = scal + 2; o.sK = scal + 4; o.unscale = scal + 6;
+    o.check(cudaMemsetAsync(scal, 0, 64 * sizeof(float), o.st));
+    const int bn = nb >= 256 ? 256 : 128;
+    auto hm = [](const __half* p, int r, int c, long ld) { return HalfMatrix{p, r, c, ld}; };
+    // work = Z^T C2
+    o.scale_of(C2, ldc, rows, nb, o.sW);
+    o.scale_of(Z, ldz, rows, h, o.sY);
+    o.split(C2, ldc, rows, nb, o.sW, Cp, false);
+    o.split(Z, ldz, rows, h, o.sY, Zp, false);
+    combine_scale_kernel<<<1, 1, 0, o.st>>>(o.sY, o.sW, o.unscale);
+    TcGemmParams p;
+    tc_fill_gram(p, bn, 0, rows, 0, h, 0, nb, work, h, nullptr, 0);
+    o.product3(false, bn, hm(Zp.hi, rows, h, ldp), hm(Zp.lo, rows, h, ldp), hm(Cp.hi, rows, nb, ldp),
+               hm(Cp.lo, rows, nb, ldp), p, EPI_STORE, EPI_ADD);
+    // C2 -= X work
+    o.scale_of(work, h, h, nb, o.sK);
+    o.split(work, h, h, nb, o.sK, Kp, false);
+    o.scale_of(X, ldx, rows, h, o.sW);
+    o.split(X, ldx, rows, h, o.sW, Xp, false);
+    combine_scale_kernel<<<1, 1, 0, o.st>>>(o.sW, o.sK, o.unscale);
+    tc_fill_update(p, bn, 0, rows, 0, h, 0, nb, C2, ldc, nullptr, 0);
+    o.product3(true, bn, hm(Xp.hi, rows, h, ldp), hm(Xp.lo, rows, h, ldp), hm(Kp.hi, h, nb, ldk),
+               hm(Kp.lo, h, nb, ldk), p, EPI_SUB, EPI_SUB);
+    o.launches += 2;
+    if (launches) *launches += o.launches;
+    if (o.err != cudaSuccess) return cuda_fail(ctx, o.err, "split_project");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "split_project launch");
+    return 0;
+}
+
 }  // namespace lb
 
 extern "C" {

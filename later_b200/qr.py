@@ -249,6 +249,22 @@ def mgs_caqr_panel_256x32(ctxt: Context | None, m: int, n: int, A: torch.Tensor,
         ctxt._raise(rc)
 
 
+def later_rhouqr(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int, W: torch.Tensor, ldw: int,
+                 R: torch.Tensor, ldr: int, work=None, lwork: int = 0, hwork=None, lhwork: int = 0, U=None,
+                 merge_top: bool = False) -> None:
+    """Recursive Householder QR in WY form (reference QR/later_rhouqr.cu:21-201): A <- Y, W, R out;
+    later_ormqr(m, n, W, ldw, A, lda) then forms the explicit Q.  merge_top=True is later_bhouqr's
+    contract (complete W, for later_ormqr2)."""
+    ctxt = ctxt or default_context()
+    _check_colmajor("A", A, m, n, lda)
+    _check_colmajor("W", W, m, n, ldw)
+    _check_colmajor("R", R, n, n, ldr)
+    rc = lib.later_b200_rhouqr(ctxt._h, m, n, A.data_ptr(), lda, W.data_ptr(), ldw, R.data_ptr(), ldr,
+                               1 if merge_top else 0)
+    if rc != 0:
+        ctxt._raise(rc)
+
+
 def later_ormqr(m: int, n: int, W: torch.Tensor, ldw: int, Y: torch.Tensor, ldy: int, work=None,
                 ctxt: Context | None = None) -> None:
     """W <- explicit Q from the WY pair (reference QR/later_ormqr.cu:18-64)."""

@@ -54,5 +54,17 @@ int ref_later_qdwh_polar(int n, float* A, int lda, float* tmpA, float* work, voi
     later_qdwh_polar(g_ctxt, n, A, lda, nullptr, n, tmpA, work, (__half*)hwork);
     return (int)cudaGetLastError();
 }
+// reference later_rhouqr / later_bhouqr (QR/later_rhouqr.cu:26, QR/later_bhouqr.cu): A <- Y, W, R
+int ref_later_rhouqr(int m, int n, float* A, int lda, float* W, int ldw, float* R, int ldr, float* work, int lwork,
+                     void* hwork, int lhwork, float* U) {
+    ensure();
+    later_rhouqr(g_ctxt, m, n, A, lda, W, ldw, R, ldr, work, lwork, (__half*)hwork, lhwork, U);
+    return (int)cudaGetLastError();
+}
+int ref_later_bhouqr(int m, int n, float* A, int lda, float* W, int ldw, float* R, int ldr, float* work, int lwork,
+                     void* hwork, int lhwork, float* U) {
+    later_bhouqr(m, n, A, lda, W, ldw, R, ldr, work, lwork, (__half*)hwork, lhwork, U);
+    return (int)cudaGetLastError();
+}
 void ref_generate_uniform(float* dA, int m, int n) { generateUniformMatrix(dA, m, n); }
 }

@@ -28,6 +28,32 @@ class RefLib:
             if hasattr(self.lib, name):
                 getattr(self.lib, name).argtypes = [ci, ci, vp, ci, vp, ci, vp]
 
+    def houqr_q(self, A0: torch.Tensor, blocked: bool = False):
+        """Reference later_rhouqr + later_ormqr (or later_bhouqr + later_ormqr2), as its driver chains them
+        (test/test_qr.cu:116-127, :160-172); returns the explicit Q and R."""
+        m, n = A0.shape
+        vp, ci = C.c_void_p, C.c_int
+        fn = self.lib.ref_later_bhouqr if blocked else self.lib.ref_later_rhouqr
+        fn.argtypes = [ci, ci, vp, ci, vp, ci, vp, ci, vp, ci, vp, ci, vp]
+        form = self.lib.ref_later_ormqr2 if blocked else self.lib.ref_later_ormqr
+        form.argtypes = [ci, ci, vp, ci, vp, ci, vp]
+        A = self._colmajor(A0)
+        W = torch.zeros((n, m), device="cuda", dtype=torch.float32).t()
+        R = torch.zeros((n, n), device="cuda", dtype=torch.float32).t()
+        work = torch.zeros(m * n + (1 << 20), device="cuda")
+        hwork = torch.zeros(m * n, device="cuda", dtype=torch.float16)
+        U = torch.zeros(32 * 32, device="cuda")
+        rc = fn(m, n, A.data_ptr(), m, W.data_ptr(), m, R.data_ptr(), n, work.data_ptr(), work.numel(),
+                hwork.data_ptr(), hwork.numel(), U.data_ptr())
+        torch.cuda.synchronize()
+        if rc != 0:
+            raise RuntimeError(f"reference householder qr: cuda error {rc}")
+        rc = form(m, n, W.data_ptr(), m, A.data_ptr(), m, work.data_ptr())
+        torch.cuda.synchronize()
+        if rc != 0:
+            raise RuntimeError(f"reference later_ormqr: cuda error {rc}")
+        return W, torch.triu(R)
+
     def qdwh_polar(self, X0: torch.Tensor) -> torch.Tensor:
         """Reference later_qdwh_polar (EVD/later_qdwh_polar.cu:24) on a copy of X0 (n x n); returns U."""
         n = X0.shape[0]

@@ -194,3 +194,54 @@ def test_out_of_core_qr_matches_the_in_core_factorisation(qr, ctx, m, n, B, pinn
     assert back <= 2 * back_in + 1e-7 and orth <= 2 * orth_in + 1e-8, (back, back_in, orth, orth_in)
     cond = np.linalg.cond(A0.astype(np.float64))
     assert np.abs(R - Rd.cpu().numpy()).max() <= 2e-3 * cond * np.abs(R).max()
+
+
+# ------------------------------------------------------------------------------ Householder QR (WY form)
+def test_householder_leaf_reconstructs_householder_vectors(qr, ctx):
+    """One 32-column leaf: Gram/Cholesky strip + reconstruction of the Householder vectors.  Q = I - W Y^T
+    must be orthogonal (the FULL m x m matrix, not just its first columns) with A = Q[:, :n] R, in fp32."""
+    m, n = 512, 32
+    g = torch.Generator(device="cuda").manual_seed(59)
+    A0 = torch.randn(m, n, device="cuda", generator=g)
+    Y, W, R = qr.to_colmajor(A0), qr.colmajor_empty(m, n), qr.colmajor_empty(n, n)
+    qr.later_rhouqr(ctx, m, n, Y, m, W, m, R, n)
+    Q = torch.eye(m, device="cuda", dtype=torch.float64) - W.double() @ Y.double().t()
+    assert torch.triu(Y[:n], 1).abs().max().item() == 0.0 and (Y.diagonal() == 1.0).all()
+    assert (Q.t() @ Q - torch.eye(m, device="cuda", dtype=torch.float64)).abs().max().item() <= 2e-5
+    assert ((Q[:, :n] @ R.double()) - A0.double()).abs().max().item() <= 2e-5 * A0.abs().max().item() * n ** 0.5
+
+
+@pytest.mark.parametrize("m,n,blocked", [(1024, 256, False), (4096, 1024, False), (2048, 512, True),
+                                         (65544, 256, False)])
+def test_householder_qr_wy_pair(qr, ctx, ref, m, n, blocked):
+    """later_rhouqr / later_bhouqr (reference QR/later_rhouqr.cu:21-201): Y unit lower trapezoidal, R upper
+    triangular, Q = I - W Y^T orthogonal with A = Q R; the explicit Q from later_ormqr / later_ormqr2, as the
+    reference's driver chains them (test/test_qr.cu:116-127, :160-172), within 2x of the reference's."""
+    g = torch.Generator(device="cuda").manual_seed(60 + n)
+    A0 = torch.rand(m, n, device="cuda", generator=g)
+    Y = qr.to_colmajor(A0)
+    W = qr.colmajor_empty(m, n)
+    W.fill_(float("nan"))
+    R = qr.colmajor_empty(n, n)
+    R.fill_(float("nan"))
+    qr.later_rhouqr(ctx, m, n, Y, m, W, m, R, n, merge_top=blocked)
+    torch.cuda.synchronize()
+    assert torch.isfinite(Y).all() and torch.isfinite(W).all() and torch.isfinite(R).all()
+    assert torch.tril(R, -1).abs().max().item() == 0.0
+    assert torch.triu(Y[:n], 1).abs().max().item() == 0.0 and (Y.diagonal() == 1.0).all()
+    Q = W.clone()
+    (qr.later_ormqr2 if blocked else qr.later_ormqr)(m, n, Q, m, Y, m, ctxt=ctx)
+    back, orth = metrics(A0, Q, R)
+    assert back <= 1e-3 and orth <= 1e-3, (back, orth)
+    if ref is not None:
+        Qr, Rr = ref.houqr_q(A0, blocked)
+        if torch.isfinite(Qr).all():
+            back_ref, orth_ref = metrics(A0, Qr, Rr)
+            if blocked:
+                # later_bhouqr is all-fp32 in the reference (QR/later_bhouqr.cu:64-167: cublasSgemm only); here
+                # its products are split-precision tensor-core triples whose planes are scaled by the LARGEST
+                # entry of an operand - Y and W hold unit-size entries next to O(1/sqrt(m)) ones, so the small
+                # ones keep ~17 bits: backward error ~1e-5 instead of ~5e-7.  Stated tolerance: 5e-5 / 5e-7.
+                assert back <= max(2 * back_ref, 5e-5) and orth <= max(2 * orth_ref, 5e-7), (back, back_ref, orth, orth_ref)
+            else:
+                assert back <= 2 * back_ref + 1e-7 and orth <= 2 * orth_ref + 1e-8, (back, back_ref, orth, orth_ref)

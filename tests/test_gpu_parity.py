@@ -568,8 +568,8 @@ def _parse_driver(out: str):
     return back, orth
 
 
-@pytest.mark.parametrize("m,n", [(1024, 1024), (4096, 2048)])
-def test_reference_driver_runs_unchanged_against_this_library(m, n):
+@pytest.mark.parametrize("algo,m,n", [(1, 1024, 1024), (1, 4096, 2048), (2, 2048, 1024), (3, 2048, 1024)])
+def test_reference_driver_runs_unchanged_against_this_library(algo, m, n):
     """test/test_qr.cu of the reference, compiled unmodified: once with the reference's own sources
     (test_qr_ref) and once against later_b200 (test_qr_b200); same cuRAND input (seed 3000)."""
     ref_bin, new_bin = ROOT / "oracle/_ref/test_qr_ref", ROOT / "oracle/_ref/test_qr_b200"
@@ -577,8 +577,16 @@ def test_reference_driver_runs_unchanged_against_this_library(m, n):
         pytest.skip("oracle/_ref binaries not built (need /root/reference at build time)")
     outs = []
     for exe in (ref_bin, new_bin):
-        r = subprocess.run([str(exe), "1", str(m), str(n), "-check"], capture_output=True, text=True, timeout=600)
+        r = subprocess.run([str(exe), str(algo), str(m), str(n), "-check"], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         outs.append(_parse_driver(r.stdout))
     (back_ref, orth_ref), (back_new, orth_new) = outs
-    assert back_new <= 2 * back_ref and orth_new <= 2 * orth_ref, outs
+    if algo == 1:
+        assert back_new <= 2 * back_ref and orth_new <= 2 * orth_ref, outs
+    else:
+        # algo 2 / 3: later_rhouqr + later_ormqr / later_bhouqr + later_ormqr2.  (The reference's current
+        # later_rhouqr merges the top-level W block itself AND its driver's later_ormqr merges it again -
+        # the guard at QR/later_rhouqr.cu:165 is commented out - so its own numbers may be off; the bar
+        # here is absolute as well.)
+        assert back_new <= max(2 * back_ref, 1e-3) and orth_new <= max(2 * orth_ref, 1e-3), outs
+        assert np.isfinite(back_new) and np.isfinite(orth_new)
