@@ -128,6 +128,17 @@ int later_b200_tsqr_apply(later_b200_ctx* ctx, int m, int n, float* Q, int ldq, 
  *                          whatever means it has; every rank calls later_b200_comm_init
  *   one process, P GPUs:   later_b200_comm_init_all over the P contexts (one host thread per context
  *                          then calls later_b200_rgsqrf_dist, or see later_b200_rgsqrf_mgpu below) */
+/* Optional, on top of the communicator: an NVLink peer-memory path for the all-reduces (they are small -
+ * 80 KB per panel, at most a few MB per R12 block - and latency-bound: ~5 us per call instead of NCCL's
+ * ~33 us at 8 GPUs).  Every rank allocates a slab and exports its CUDA IPC handle (64 bytes); the ranks
+ * exchange the handles by whatever means they have and import all of them, in rank order.  Messages
+ * larger than max_message_bytes keep going through NCCL.  later_b200_comm_init_all / later_b200_mgpu_create
+ * set the same up with plain peer access. */
+#define LATER_B200_PEER_HANDLE_BYTES 64
+int later_b200_peer_export(later_b200_ctx* ctx, size_t max_message_bytes, void* handle64);
+int later_b200_peer_import(later_b200_ctx* ctx, int nranks, int rank, const void* handles);
+int later_b200_peer_init_all(later_b200_ctx* const* ctxs, int nranks, size_t max_message_bytes);
+
 #define LATER_B200_COMM_ID_BYTES 128
 int later_b200_comm_unique_id(void* id128);
 int later_b200_comm_init(later_b200_ctx* ctx, int nranks, int rank, const void* id128);

@@ -39,6 +39,9 @@ SYMBOLS = {
     "later_b200_gemm_update": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int,
                                          C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long, C.c_void_p,
                                          C.c_long, C.c_int]),
+    "later_b200_peer_export": (C.c_int, [_c_ctx, C.c_size_t, C.c_void_p]),
+    "later_b200_peer_import": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p]),
+    "later_b200_peer_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_size_t]),
     "later_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
     "later_b200_comm_init": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p]),
     "later_b200_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),

@@ -34,6 +34,7 @@ SOURCES = {
     "qdwh.cu": [],
     "hou.cu": [],
     "mgpu.cu": [],
+    "peer_comm.cu": [],
     "compat.cu": ["-rdc=true"],
 }
 

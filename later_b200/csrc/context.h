@@ -19,8 +19,27 @@ struct Options {
     int update_variant = 0;       // LB_UPDATE_VARIANT (later_b200_gemm_update only)
     int ormqr_kchunk = 2048;      // LB_ORMQR_KCHUNK
     bool gram_2cta = true;        // LB_GRAM_2CTA = 0: never use the CTA-pair Gram kernel
+    bool peer_allreduce = true;   // LB_PEER_ALLREDUCE = 0: NCCL for every all-reduce of the row-sharded path
 };
 constexpr int kGraphSlots = 4;    // cached executable graphs per entry point (LRU)
+
+// NVLink peer-memory all-reduce of the small blocks the row-sharded factorisation exchanges
+// (peer_comm.cu): every rank owns a slab that all its peers have mapped.
+struct PeerComm {
+    static constexpr int kMaxRanks = 16;
+    void* slab = nullptr;                 // this rank's slab (cudaMalloc)
+    void* peers[kMaxRanks] = {};          // every rank's slab in this rank's address space
+    bool ipc[kMaxRanks] = {};             // opened with cudaIpcOpenMemHandle (to be closed)
+    int nranks = 1, rank = 0;
+    size_t half_bytes = 0;                // largest message
+    bool ready = false;
+    size_t slab_bytes() const;
+    cudaError_t allocate(size_t max_message_bytes);
+    void release();
+    bool fits(size_t bytes) const;
+    // in-place sum over the ranks of `count` doubles / floats, same bits on every rank
+    cudaError_t allreduce(void* buf, size_t count, bool f64, cudaStream_t stream);
+};
 }  // namespace lb
 
 struct later_b200_ctx {
@@ -84,6 +103,7 @@ struct later_b200_ctx {
     lb::ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     std::shared_ptr<lb::CommGroup> comm_group;   // set when the ranks are contexts of this process
+    lb::PeerComm peer;                            // NVLink peer-memory path for the small all-reduces
     // scratch of the callers built on top of the factorisation (re-orthogonalisation, QDWH): lives
     // outside the arena, which every factorisation carves anew
     void* aux = nullptr; size_t aux_bytes = 0;

@@ -94,6 +94,8 @@ int later_b200_mgpu_create(later_b200_mgpu** out, int P, const int* devices) {
     // all-gather of the TSQR variant
     if (rc == 0 && P > 1 && (rc = later_b200_comm_init_all(g->main_ctx.data(), P)) != 0)
         g->error = later_b200_last_error(g->main_ctx[0]);
+    if (rc == 0 && P > 1 && (rc = later_b200_peer_init_all(g->main_ctx.data(), P, (size_t)4 << 20)) != 0)
+        g->error = later_b200_last_error(g->main_ctx[0]);
     if (rc == 0 && P > 1) {
         g->nccl = Nccl::get(&g->error);
         if (!g->nccl) rc = LATER_B200_ESTATE;

@@ -3,10 +3,9 @@
 //                         fp32 x fp32 products accumulated in fp64 on the fp64 tensor path
 //                         (mma.sync.m8n8k4.f64), per-CTA partial Gram blocks
 //   gram128_reduce_kernel fixed-order sum of the per-CTA partials (deterministic)
-//   chol128_kernel        R = chol(G) in fp64 on one CTA: trailing matrix in registers, two columns
-//                         per step derived inside one warp, column pairs broadcast through an
-//                         mbarrier-guarded shared-memory ring, a dedicated output warp publishes R
-//                         block-row by block-row
+//   chol128b_kernel       R = chol(G) in fp64 on one CTA, blocked by 32 columns: one warp factors each
+//                         diagonal block (two columns per step), the others solve, update (fp64
+//                         tensor path) and publish R block-row by block-row; barriers only
 //   apply128_kernel       Q = A R^-1 by forward substitution, four threads per matrix row; launched
 //                         with programmatic dependent launch so that it runs CONCURRENTLY with the
 //                         Cholesky kernel and consumes each 32-row block of R as soon as its flag is
@@ -218,30 +217,6 @@ __device__ __forceinline__ double rsqrt_f64(double x) {
     return fma(0.5 * y, e, y);                 // one Newton step: ~2^-45 relative
 }
 
-// R = chol(G)^T in fp64, one CTA: 8 compute warps + 4 output warps.
-// Compute thread (tx = column residue mod 16, ty = row residue mod 16) keeps the elements
-// (i, j) = (ty + 16 ia, tx + 16 jb), ia >= jb, of the trailing lower triangle in registers (36
-// doubles).  Warp w holds tx in {2w, 2w + 1} (one per half-warp): an even column c and its right
-// neighbour c + 1 live in the same warp, which derives BOTH with shuffles only.  Column pairs travel
-// through an 8-slot shared-memory ring (published-pair counter with release/acquire semantics for
-// "full", mbarriers for "empty") and are applied by every compute warp as
-// rank-2 updates; four more warps do nothing but write finished columns (rows of R, the 32x32
-// factor blocks, 1/diag, the block-row flags) to global memory, so no compute warp ever leaves the
-// register/shared-memory domain and nobody waits at a block-wide barrier.
-constexpr int CHOL_RING = 8;            // ring slots (column pairs in flight)
-
-struct CholShared {
-    double col[CHOL_RING][2][PW];
-    double rs[PW];              // 1 / L(c, c), written by the owner before it publishes column c
-    double gdiag[PW];           // G(c, c), for the pivot-ratio check of the output warps
-    uint64_t empty[CHOL_RING];  // mbarriers: all readers of a slot are done
-    int published;              // number of column pairs published so far (release / acquire)
-    int bad;                    // 1 + local column of the first non-positive pivot (0 = none)
-#ifdef LB_CHOL_TRACE
-    long long tr[64][8];        // per pair: owner timestamps
-#endif
-};
-
 struct CholOut {
     float* R; long ldr;
     PanelFactors* fac;
@@ -252,250 +227,19 @@ struct CholOut {
     double tau;         // pivot-ratio threshold of that check
 };
 
-__device__ __forceinline__ void chol_publish(int* counter, int value) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(counter)), "r"(value) : "memory");
-}
-// Spin until `value` pairs have been published.  A plain acquire load is polled instead of an
-// mbarrier: waking up from mbarrier.try_wait costs ~160 cycles on the serial chain, a shared-memory
-// load ~30.
-__device__ __forceinline__ void chol_wait_published(const int* counter, int value) {
-    int v;
-    unsigned long long n = 0;
-    do {
-        asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(counter)) : "memory");
-        if (++n > (unsigned long long)(LB_SPIN_LIMIT)) __trap();   // protocol bug: fail, do not hang
-    } while (v < value);
-}
-
-constexpr int CHOL_OUT_WARPS = 4;                 // output warp j writes rows 32 j .. 32 j + 31
-constexpr int CHOL_THREADS = (8 + CHOL_OUT_WARPS) * 32;
-
-// Derives columns c (even) and c + 1 and publishes the pair.  This is the serial chain of the
-// factorisation, so the two reciprocal square roots are made independent of each other:
-//   piv1 = a11 - a10^2 / piv0 = d / piv0,  d = a11 piv0 - a10^2
-//   => rsqrt(piv1) = rsqrt(d) * sqrt(piv0), and rsqrt(d), rsqrt(piv0) start together.
-template <int CB>
-__device__ __forceinline__ void chol_emit_pair(double (&a)[8][8], int c, int ty, int lane,
-                                               CholShared& sh, const CholOut& o) {
-    const int cr = c & 15;                     // even; column c lives in half-warp 0, c+1 in half 1
-    const int half = lane >> 4;
-    const double piv0 = __shfl_sync(0xffffffffu, a[CB][CB], cr);            // (c, c)
-    const double a10 = __shfl_sync(0xffffffffu, a[CB][CB], cr + 1);         // (c+1, c)
-    const double a11 = __shfl_sync(0xffffffffu, a[CB][CB], 16 + cr + 1);    // (c+1, c+1)
-    double u[8];                               // unscaled column c, same row, for half-warp 1
-#pragma unroll
-    for (int ia = CB; ia < 8; ++ia) u[ia] = __shfl_sync(0xffffffffu, a[ia][CB], ty);
-    const double d = fma(a11, piv0, -a10 * a10);
-    const bool bad0 = !(piv0 > 0.0);
-    const bool bad1 = !(d > 0.0);
-    const double p0 = bad0 ? 1e-300 : piv0;
-    const double rs0 = rsqrt_f64(p0);
-    const double rd = rsqrt_f64(bad1 ? 1e-300 : d);
-    const double rs1 = rd * (p0 * rs0);        // rsqrt(piv1)
-    const double w = a10 * rs0 * rs0;          // L(c+1, c) / L(c, c)
-    const int slot = (c >> 1) & (CHOL_RING - 1);
-#pragma unroll
-    for (int ia = 0; ia < 8; ++ia) {
-        double l = 0.0;
-        if (ia >= CB) l = half ? fma(-u[ia], w, a[ia][CB]) * rs1 : a[ia][CB] * rs0;
-        if (ia == CB && ty < cr + half) l = 0.0;          // rows above the diagonal
-        sh.col[slot][half][ty + 16 * ia] = l;
-    }
-    if (lane == 0) { sh.rs[c] = rs0; sh.rs[c + 1] = rs1; }
-    __syncwarp();
-    if (lane == 0) chol_publish(&sh.published, (c >> 1) + 1);
-    if (lane == 0 && (bad0 || bad1)) atomicCAS(&sh.bad, 0, c + (bad0 ? 1 : 2));   // off the chain
-}
-
-template <int CB>
-__device__ __forceinline__ void chol_block_column(double (&a)[8][8], int warp, int tx, int ty,
-                                                  int lane, CholShared& sh, const CholOut& o) {
-#pragma unroll 1
-    for (int cr = (CB == 0 ? 2 : 0); cr < 16; cr += 2) {
-        const int c = CB * 16 + cr;            // pair (c, c+1) to derive; pair (c-2, c-1) to apply
-        const int ps = ((c >> 1) - 1) & (CHOL_RING - 1);     // ring slot of the previous pair
-        const int owner = cr >> 1;
-        // the owner makes sure its ring slot is free (readers of pair c/2 - 4 are done) while it
-        // would be waiting for the previous pair anyway
-#ifdef LB_CHOL_TRACE
-        const long long t0 = clock64();
-#endif
-        if (warp == owner && c >= 2 * CHOL_RING)
-            mbar_wait(smem_u32(&sh.empty[(c >> 1) & (CHOL_RING - 1)]), (((c >> 1) / CHOL_RING) & 1) ^ 1u);
-#ifdef LB_CHOL_TRACE
-        const long long t1 = clock64();
-#endif
-        chol_wait_published(&sh.published, c >> 1);                  // previous pair published
-#ifdef LB_CHOL_TRACE
-        const long long t2 = clock64();
-#endif
-        double ci0[8], ci1[8], cj0[8], cj1[8];
-#pragma unroll
-        for (int q = CB; q < 8; ++q) {
-            ci0[q] = sh.col[ps][0][ty + 16 * q];
-            ci1[q] = sh.col[ps][1][ty + 16 * q];
-            cj0[q] = sh.col[ps][0][tx + 16 * q];
-            cj1[q] = sh.col[ps][1][tx + 16 * q];
-        }
-        // block column CB first (it contains columns c, c+1) so that its owner can derive them
-#pragma unroll
-        for (int ia = CB; ia < 8; ++ia)
-            a[ia][CB] = fma(-ci1[ia], cj1[CB], fma(-ci0[ia], cj0[CB], a[ia][CB]));
-#ifdef LB_CHOL_TRACE
-        const long long t3 = clock64();
-#endif
-        if (warp == owner) chol_emit_pair<CB>(a, c, ty, lane, sh, o);
-#ifdef LB_CHOL_TRACE
-        const long long t4 = clock64();
-#endif
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sh.empty[ps]));        // done reading the previous pair
-        // rest of the rank-2 update
-#pragma unroll
-        for (int jb = CB + 1; jb < 8; ++jb)
-#pragma unroll
-            for (int ia = jb; ia < 8; ++ia)
-                a[ia][jb] = fma(-ci1[ia], cj1[jb], fma(-ci0[ia], cj0[jb], a[ia][jb]));
-#ifdef LB_CHOL_TRACE
-        if (warp == owner && lane == 0) {
-            long long* r = sh.tr[c >> 1];
-            r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3; r[4] = t4; r[5] = clock64();
-        }
-#endif
-    }
-}
-
-// The output warps: column k of L = row k of R -> caller's R (strictly lower part written as zero),
-// the 32 x 32 factor blocks (columns permuted for the apply kernel), 1/diag; output warp j owns the
-// rows i = 32 j + lane; warp 0 also raises flag[b] when block-row b is complete (after a named
-// barrier among the output warps, so that all of their global writes precede the flag).
-__device__ __forceinline__ void chol_output_warp(int j, int lane, CholShared& sh, const CholOut& o) {
-    const int pl = perm32(lane);
-    const int i = lane + 32 * j;
-    double min_ratio = 1.0;                // lanes 0, 1 of output warp 0: min piv_k / G_kk so far
-#pragma unroll 1
-    for (int s = 0; s < PW / 2; ++s) {
-        const int slot = s & (CHOL_RING - 1);
-        chol_wait_published(&sh.published, s + 1);
-#pragma unroll
-        for (int hcol = 0; hcol < 2; ++hcol) {
-            const int k = 2 * s + hcol, rb = k >> 5, rr = k & 31;
-            const float l = i < k ? 0.f : (float)sh.col[slot][hcol][i];
-            o.R[k + (long)i * o.ldr] = l;                           // R(k, i) = L(i, k)
-            if (i >= k) {
-                if (j == rb) o.fac->Rdiag[rb][rr][pl] = l;
-                else o.fac->Roff[off_index(rb, j)][rr][pl] = l;
-            }
-        }
-        if (j == 0 && lane < 2) {
-            const double rs = sh.rs[2 * s + lane];
-            o.fac->rinv[2 * s + lane] = (float)rs;
-            const double gd = sh.gdiag[2 * s + lane];
-            // piv / G_kk = 1 / (rs^2 G_kk); a zero or non-finite G_kk counts as breakdown
-            const double ratio = (gd > 0.0 && gd < 1e300) ? 1.0 / (rs * rs * gd) : 0.0;
-            min_ratio = fmin(min_ratio, ratio);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sh.empty[slot]));
-        if ((s & 15) == 15) {                  // columns 32 b .. 32 b + 31 are out: publish block-row b
-            __threadfence();
-            asm volatile("bar.sync 3, %0;" ::"n"(CHOL_OUT_WARPS * 32) : "memory");
-            if (j == 0 && lane == 0) *reinterpret_cast<volatile int*>(&o.fac->flag[s >> 4]) = 1;
-        }
-    }
-    // Status of the panel (every column has been published, so sh.bad is final).
-    if (j == 0) {
-        const double other = __shfl_sync(0xffffffffu, min_ratio, 1);
-        if (lane == 0) {
-            min_ratio = fmin(min_ratio, other);
-            const int bad = *reinterpret_cast<volatile int*>(&sh.bad);
-            if (o.check_redo) {
-                o.info[INFO_REDO] = (bad != 0 || !(min_ratio >= o.tau)) ? 1 : 0;
-            } else {
-                if (bad != 0) atomicCAS(&o.info[INFO_BAD_COLUMN], 0, o.col0 + bad);
-                int e = 0;
-                if (min_ratio > 0.0) { frexp(min_ratio, &e); e = 1 - e; } else { e = 2047; }
-                atomicMax(&o.info[INFO_COND_LOG2], e);      // ~ -log2(min ratio), rounded up
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(CHOL_THREADS, 1)
-chol128_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr,
-               PanelFactors* __restrict__ fac, int* __restrict__ info, int col0, int check_redo,
-               double tau, const int* __restrict__ cond) {
-    __shared__ CholShared sh;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = 2 * warp + (lane >> 4);      // column residue (compute warps)
-    const int ty = lane & 15;                   // row residue
-    const CholOut o{R, ldr, fac, info, col0, check_redo, tau};
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < CHOL_RING; ++s) mbar_init(smem_u32(&sh.empty[s]), 8 + CHOL_OUT_WARPS);
-        sh.published = 0;
-        sh.bad = 0;
-        fence_barrier_init();
-    }
-    pdl_wait();      // G and the cleared flags come from the reduce kernel
-    if (cond) {      // fallback launch: runs only if the first attempt asked for it
-        if (*cond == 0) return;
-        if (threadIdx.x == 0) { atomicAdd(&info[INFO_FALLBACKS], 1); atomicOr(&info[INFO_FLAGS], 2); }
-    }
-    if (warp >= 8) {
-        const int k = threadIdx.x - 256;
-        sh.gdiag[k] = gram_elem(G, k, k);
-    }
-    // Only now may the dependent apply grid start: it synchronises on fac->flag[] (not on the
-    // completion of this grid), so the flags must already have been cleared by the reduce kernel.
-    pdl_trigger();
-    __syncthreads();
-    if (warp >= 8) {
-        chol_output_warp(warp - 8, lane, sh, o);
-        return;
-    }
-    double a[8][8];
-#pragma unroll
-    for (int ia = 0; ia < 8; ++ia)
-#pragma unroll
-        for (int jb = 0; jb < 8; ++jb) {
-            const int i = ty + 16 * ia, j = tx + 16 * jb;
-            a[ia][jb] = (ia >= jb && i >= j) ? gram_elem(G, i, j) : 0.0;
-        }
-    if (warp == 0) chol_emit_pair<0>(a, 0, ty, lane, sh, o);   // columns 0, 1 need no update
-    chol_block_column<0>(a, warp, tx, ty, lane, sh, o);
-    chol_block_column<1>(a, warp, tx, ty, lane, sh, o);
-    chol_block_column<2>(a, warp, tx, ty, lane, sh, o);
-    chol_block_column<3>(a, warp, tx, ty, lane, sh, o);
-    chol_block_column<4>(a, warp, tx, ty, lane, sh, o);
-    chol_block_column<5>(a, warp, tx, ty, lane, sh, o);
-    chol_block_column<6>(a, warp, tx, ty, lane, sh, o);
-    chol_block_column<7>(a, warp, tx, ty, lane, sh, o);
-#ifdef LB_CHOL_TRACE
-    asm volatile("bar.sync 2, 256;");
-    if (threadIdx.x == 0) {
-        for (int cb = 0; cb < 8; ++cb) {
-            long long e = 0, f = 0, l = 0, em = 0, rest = 0, per = 0; int n = 0;
-            for (int sidx = cb * 8 + (cb == 0 ? 2 : 0); sidx < cb * 8 + 8; ++sidx) {
-                const long long* r = sh.tr[sidx];
-                e += r[1] - r[0]; f += r[2] - r[1]; l += r[3] - r[2]; em += r[4] - r[3]; rest += r[5] - r[4];
-                per += r[4] - sh.tr[sidx - 1][4]; ++n;
-            }
-            printf("CB %d owner: empty-wait %lld full-wait %lld lds+blockcol %lld emit %lld rest %lld | emit-to-emit %lld\n",
-                   cb, e / n, f / n, l / n, em / n, rest / n, per / n);
-        }
-    }
-#endif
-}
-
 // ---------------------------------------------------------------------------------------------
 // R = chol(G)^T in fp64, one CTA, blocked (32-column blocks), synchronised with barriers only.
 //
 // Per block step b:
 //   warp 0          factors the 32 x 32 diagonal block entirely by itself: lane i owns row i in
 //                   registers, two columns per step (the two reciprocal square roots independent of
-//                   each other, as in chol_emit_pair), the column pair broadcast to the other lanes
-//                   through 512 bytes of shared memory behind a __syncwarp - ~200 cycles per pair
-//                   where the ring-and-poll protocol of chol128_kernel needs ~840
+//                   each other), the column pair broadcast to the other lanes through 512 bytes of
+//                   shared memory behind a __syncwarp: ~425 cycles per pair (a chain of ~10 dependent
+//                   fp64 operations at ~20 cycles each plus the shuffle / shared-memory round trip), where
+//                   round 1's register-resident kernel with its cross-warp publish / poll ring needed ~840.
+//                   (That kernel is gone: the two were equally fast end to end - the trailing updates on
+//                   a single SM's fp64 pipe bound both - but compute-sanitizer racecheck cannot model its
+//                   ld.acquire / st.release protocol and reported hazards; this one is clean.)
 //   warps 1 .. 11   meanwhile finish step b - 1: the rest of its trailing update and its output (32 rows
 //                   of R, the factor blocks of the apply kernel, 1/diag, the block-row flag)
 //   all             triangular solve of the rows below (one row per thread), then the update of the NEXT
@@ -1005,13 +749,8 @@ cudaError_t panel_init() {
     return e != cudaSuccess ? e : tc_apply_init();
 }
 
-// The panel's Cholesky factorisation: blocked barrier-synchronised kernel, or (LB_CHOL = 1, for
-// comparison) the register-resident ring-and-poll kernel of round 1.
-static cudaError_t launch_chol(cudaStream_t stream, const PanelOpts& opts, const double* G, float* R, long ldr,
+static cudaError_t launch_chol(cudaStream_t stream, const PanelOpts&, const double* G, float* R, long ldr,
                                PanelFactors* fac, int* info, int col0, int check_redo, double tau, const int* cond) {
-    if (opts.chol_variant == 1)
-        return launch_pdl(chol128_kernel, dim3(1), dim3(CHOL_THREADS), 0, stream, G, R, ldr, fac, info, col0,
-                          check_redo, tau, cond);
     return launch_pdl(chol128b_kernel, dim3(1), dim3(CH2_THREADS), sizeof(Chol2Smem), stream, G, R, ldr, fac, info,
                       col0, check_redo, tau, cond);
 }

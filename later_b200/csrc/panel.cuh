@@ -34,7 +34,6 @@ struct PanelOpts {
     // LB_I8_FALLBACK_TAU: an integer-Gram panel whose smallest Cholesky pivot ratio piv_k / G_kk falls
     // below this is factored again from the fp64 Gram matrix (see panel_qr128)
     double i8_fallback_tau = 0.0078125;
-    int chol_variant = 0;                    // LB_CHOL = 1: round 1's ring-and-poll Cholesky kernel (comparison only)
 };
 
 // Status words of a factorisation (device int[kInfoWords], cleared by the caller before the first

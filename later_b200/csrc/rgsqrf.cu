@@ -213,6 +213,10 @@ __global__ void finish_r12_kernel(const float* __restrict__ S, int h, int nb, fl
 }
 
 cudaError_t comm_allreduce(later_b200_ctx* ctx, void* buf, size_t count, int dtype, cudaStream_t stream) {
+    // small blocks (everything this factorisation exchanges unless n is huge): one launch of the NVLink
+    // peer-memory kernel (peer_comm.cu), ~5 us; NCCL (~33 us per call at 8 GPUs) for the rest
+    const size_t bytes = count * (dtype == kNcclDouble ? sizeof(double) : sizeof(float));
+    if (ctx->peer.fits(bytes) && ctx->opts.peer_allreduce) return ctx->peer.allreduce(buf, count, dtype == kNcclDouble, stream);
     if (!ctx->comm || !ctx->nccl) return cudaErrorNotReady;
     const ncclResult_t r = ctx->comm_group
         ? ctx->comm_group->allreduce(ctx->nccl, ctx->rank, buf, count, dtype, ctx->comm, stream)
@@ -556,11 +560,11 @@ void read_options(Options& o) {
     o.panel.gram_i8 = geti("LB_GRAM_I8", 1) != 0;
     o.panel.gram_i8_min_rows = geti("LB_GRAM_I8_MIN_ROWS", kI8GramMinRows);
     if (const char* v = getenv("LB_I8_FALLBACK_TAU")) o.panel.i8_fallback_tau = atof(v);
-    o.panel.chol_variant = geti("LB_CHOL", 0);
     o.gram_cast = geti("LB_GRAM_CAST", 1) != 0;
     o.update_variant = geti("LB_UPDATE_VARIANT", 0);
     o.ormqr_kchunk = std::max(64, geti("LB_ORMQR_KCHUNK", 2048) / 64 * 64);
     o.gram_2cta = geti("LB_GRAM_2CTA", 1) != 0;
+    o.peer_allreduce = geti("LB_PEER_ALLREDUCE", 1) != 0;
 }
 
 std::string rank_message(const int* info) {
@@ -646,6 +650,7 @@ int later_b200_destroy(later_b200_ctx* ctx) {
     if (ctx->dR) cudaFree(ctx->dR);
     if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
+    ctx->peer.release();
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     ctx->arena.release();
@@ -757,7 +762,8 @@ int later_b200_comm_init_all(later_b200_ctx* const* ctxs, int nranks) {
 
 int later_b200_rgsqrf_dist(later_b200_ctx* ctx, int m_local, int n, float* A, int lda, float* R, int ldr) {
     if (!ctx) return LATER_B200_EINVAL;
-    if (!ctx->comm) return fail(ctx, LATER_B200_ESTATE, "later_b200_rgsqrf_dist needs later_b200_comm_init first");
+    if (!ctx->comm && !ctx->peer.ready)
+        return fail(ctx, LATER_B200_ESTATE, "later_b200_rgsqrf_dist needs later_b200_comm_init first");
     DeviceGuard guard(ctx->device);
     if (guard.error() != cudaSuccess) return cuda_fail(ctx, guard.error(), "cudaSetDevice");
     int rc = rgsqrf_prepare(ctx, m_local, n, A, lda, R, ldr, true);

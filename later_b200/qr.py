@@ -152,7 +152,7 @@ def later_qdwh_polar(ctxt: Context | None, n: int, A: torch.Tensor, lda: int, H,
     return int(it.value)
 
 
-def comm_init(ctxt: Context, group=None) -> None:
+def comm_init(ctxt: Context, group=None, peer_message_bytes: int = 4 << 20) -> None:
     """Gives the context an NCCL communicator over the ranks of a torch.distributed group (one rank per
     GPU): rank 0 draws the NCCL unique id, torch.distributed carries its 128 bytes to the others."""
     import torch.distributed as dist
@@ -168,6 +168,18 @@ def comm_init(ctxt: Context, group=None) -> None:
     rc = lib.later_b200_comm_init(ctxt._h, world, rank, raw)
     if rc != 0:
         ctxt._raise(rc)
+    # NVLink peer-memory path for the (small, latency-bound) all-reduces: exchange the slabs' IPC handles
+    hbuf = (C.c_ubyte * 64)()
+    rc = lib.later_b200_peer_export(ctxt._h, peer_message_bytes, hbuf)
+    if rc != 0:
+        ctxt._raise(rc)
+    mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=f"cuda:{ctxt.device}")
+    allh = torch.empty(world * 64, dtype=torch.uint8, device=f"cuda:{ctxt.device}")
+    dist.all_gather_into_tensor(allh, mine, group=group)
+    rc = lib.later_b200_peer_import(ctxt._h, world, rank, bytes(allh.cpu().tolist()))
+    if rc != 0:
+        ctxt._raise(rc)
+    dist.barrier(group=group)
 
 
 def later_rgsqrf_dist(ctxt: Context, m_local: int, n: int, A: torch.Tensor, lda: int, R: torch.Tensor,

@@ -12,6 +12,7 @@ rounded to fp16 with round-to-nearest, fp32 accumulation):
     mgs_kernel2()             QR/panel.cu:246-325          256 x 32 modified Gram-Schmidt
     later_ormqr/_ormqr2()     QR/later_ormqr.cu:18-85      explicit Q from WY
     later_qdwh_polar()        EVD/later_qdwh_polar.cu:24-110  QDWH polar iteration, the caller of later_rgsqrf
+    later_rhouqr()            QR/later_rhouqr.cu:21-277    recursive Householder QR in WY form (+ panel.cu:341-378)
     check_result/check_otho   test/test_qr.cu:216-268      the driver's self-consistency metrics
 
 Third-party arithmetic: every GEMM on the path is cuBLAS (closed source; 12.9.1.4 in this image;
@@ -197,6 +198,67 @@ def later_qdwh_polar(X0: np.ndarray, smin_est: float = 0.0002070391384, max_iter
     else:
         it = max_iter
     return X, it
+
+
+def _hou_caqr_panel(A: np.ndarray) -> np.ndarray:
+    """hou_caqr_panel<256,32> (QR/panel.cu:341-378): Householder QR of every 256-row block, recursion on the
+    stacked R factors, Q_blk <- Q_blk W_blk.  In place; returns R.  The block kernel (hou_kernel3,
+    QR/panel.cu:386-558) is a textbook Householder QR that leaves the explicit Q; LAPACK's stands in for it."""
+    m, n = A.shape
+    if m <= 256:
+        q, r = np.linalg.qr(A.astype(F32))
+        A[...] = q.astype(F32)
+        return r.astype(F32)
+    nblk = (m + 255) // 256
+    stack = np.zeros((nblk * n, n), dtype=F32)
+    for b in range(nblk):
+        blk = A[b * 256:min(m, (b + 1) * 256), :]
+        q, r = np.linalg.qr(blk.astype(F32))
+        blk[...] = q.astype(F32)
+        stack[b * n:b * n + r.shape[0], :] = r
+    R = _hou_caqr_panel(stack)
+    for b in range(nblk):
+        rows = slice(b * 256, min(m, (b + 1) * 256))
+        A[rows, :] = _gemm_f32(A[rows, :], stack[b * n:(b + 1) * n, :])
+    return R
+
+
+def _rhouqr(A: np.ndarray, W: np.ndarray, R: np.ndarray, top: bool, merge_top: bool) -> None:
+    """qr() of QR/later_rhouqr.cu:54-233 on views A, W (m x n) and R (n x n)."""
+    m, n = A.shape
+    if n <= 32:
+        R[...] = np.triu(_hou_caqr_panel(A))                       # A <- Q               (:58)
+        V = np.eye(m, n, dtype=F32) - A                            # I - Q                (:61-63)
+        # reconstructY (:239-277): LU without pivoting of the top block, Y = [L; (I-Q)_2 U^-1]
+        M = V[:n].astype(F32).copy()
+        L = np.eye(n, dtype=F32)
+        for j in range(n):
+            L[j + 1:, j] = M[j + 1:, j] / M[j, j]
+            M[j + 1:, j:] -= np.outer(L[j + 1:, j], M[j, j:]).astype(F32)
+        U = np.triu(M)
+        A[:n] = L
+        A[n:] = np.linalg.solve(U.T.astype(np.float64), V[n:].T.astype(np.float64)).T.astype(F32)
+        W[...] = np.linalg.solve(L.astype(np.float64), V.T.astype(np.float64)).T.astype(F32)   # (I-Q) L^-T (:67-74)
+        return
+    h = n // 2
+    _rhouqr(A[:, :h], W[:, :h], R[:h, :h], False, merge_top)
+    mul = _gemm_f32 if (h <= 128 or m <= 128) else (lambda a, b: _gemm_tc(s2h(a), s2h(b)))   # (:83, :104-137)
+    A[:, h:] -= mul(A[:, :h], mul(W[:, :h].T, A[:, h:]))           # A2 <- Q1^T A2
+    _rhouqr(A[h:, h:], W[h:, h:], R[h:, h:], False, merge_top)
+    R[:h, h:] = A[:h, h:]                                          # (:152-154)
+    A[:h, h:] = 0
+    if not top or merge_top:       # (the guard the reference has commented out at :165; its driver's
+        W[:, h:] -= mul(W[:, :h], mul(A[:, :h].T, W[:, h:]))       # later_ormqr performs the top merge)
+
+
+def later_rhouqr(A: np.ndarray, merge_top: bool = False):
+    """Returns (Y, W, R): A = (I - W Y^T) R, Y unit lower trapezoidal (QR/later_rhouqr.cu:26-41)."""
+    Y = np.array(A, dtype=F32, order="F", copy=True)
+    m, n = Y.shape
+    W = np.zeros((m, n), dtype=F32, order="F")
+    R = np.zeros((n, n), dtype=F32, order="F")
+    _rhouqr(Y, W, R, True, merge_top)
+    return Y, W, R
 
 
 def check_result(A: np.ndarray, Q: np.ndarray, R: np.ndarray) -> float:

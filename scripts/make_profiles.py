@@ -37,7 +37,8 @@ for rep in sorted((ROOT / "gpurun_out").glob("*.ncu-rep")):
             for k in KEYS:
                 if k in d:
                     f.write(f"  {k:72s} {d[k]}\n")
-    if rep.stem == "prof_gram8192" and rows:
+    if rep.stem in ("prof_gram8192", "prof_gram16k") and rows:
+        rows = sorted(rows, key=lambda d: -float(d["gpu__time_duration.sum"].split()[0].replace(",", "")))   # the top-level one
         def num(s):
             v, u = s.split()[0], s.split()[1] if len(s.split()) > 1 else ""
             mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
@@ -45,6 +46,8 @@ for rep in sorted((ROOT / "gpurun_out").glob("*.ncu-rep")):
         traffic["tc_gemm_gram_top_bytes"] = num(rows[0]["dram__bytes_read.sum"]) + num(rows[0]["dram__bytes_write.sum"])
         traffic["tc_gemm_gram_top_tensor_pipe_pct"] = rows[0]["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]
 if traffic:
+    import datetime
+    traffic["source"] = f"profiles/{tag}_ncu_gram16k.txt (ncu --set full, {datetime.date.today().isoformat()})"
     (OUT / "traffic.json").write_text(json.dumps(traffic, indent=1))
 for name in ("launches_16k", "launches_1m", "launches_256k"):
     src = ROOT / "gpurun_out" / f"{name}.csv"

@@ -274,10 +274,10 @@ def test_integer_gram_vs_fp64_gram(qr, m, n, dist, monkeypatch):
         out[i8] = (A, R, c.last_launch_count)
         c.close()
     (Q0, R0, l0), (Q1, R1, l1) = out["0"], out["1"]
-    # per panel: the integer Gram kernel, three conditional fp64 fallback launches and the conditional
-    # forward-substitution apply, plus a column-maxima pass unless the update that produced the panel
-    # left them behind
-    assert l0 + 5 * (n // 128) <= l1 <= l0 + 6 * (n // 128)
+    # per panel: three conditional fp64 fallback launches and the conditional forward-substitution apply on
+    # top of the fp64 path's five (the integer Gram kernel replaces the fp64 one), plus one column-maxima
+    # pass for the first panel (the update that produces a later panel leaves its maxima behind)
+    assert l1 == l0 + 4 * (n // 128) + 1
     assert (R1 - R0).abs().max().item() <= 5e-6 * R0.abs().max().item()
     # (a last-bit change of R12 can flip fp16 roundings of the update's operands: Q moves at that level)
     assert (Q1 - Q0).abs().max().item() <= 4.9e-4 * Q0.abs().max().item()

@@ -134,3 +134,18 @@ def test_oracle_qdwh_polar_converges_to_the_polar_factor():
     assert np.abs(U - Ue).max() <= 5e-2
     assert np.linalg.norm(U.astype(np.float64).T @ U - np.eye(n)) / n <= 1e-4
     assert np.abs(U - U.T).max() == 0.0
+
+
+@pytest.mark.parametrize("m,n", [(300, 32), (512, 128), (1024, 512)])
+def test_oracle_rhouqr_is_a_householder_factorisation(m, n):
+    """later_rhouqr (QR/later_rhouqr.cu:21-277) restated: Y unit lower trapezoidal, Q = I - W Y^T orthogonal
+    once later_ormqr has merged the two halves of W (QR/later_ormqr.cu:27-45), A = Q R."""
+    rng = np.random.default_rng(8)
+    A = rng.random((m, n), dtype=np.float32)
+    Y, W, R = orc.later_rhouqr(A)
+    assert np.abs(np.triu(Y[:n], 1)).max() == 0.0 and np.all(np.diag(Y) == 1.0)
+    assert np.abs(np.tril(R, -1)).max() == 0.0
+    Q = orc.later_ormqr(W, Y) if n >= 64 else orc.later_ormqr2(W, Y)
+    tol = 1e-3 if n > 256 else 2e-5          # fp16 products only where n/2 > 128 (QR/later_rhouqr.cu:83)
+    assert orc.check_result(A, Q, R) <= tol
+    assert orc.check_otho(Q) <= tol
