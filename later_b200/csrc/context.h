@@ -38,7 +38,8 @@ struct PeerComm {
     void release();
     bool fits(size_t bytes) const;
     // in-place sum over the ranks of `count` doubles / floats, same bits on every rank
-    cudaError_t allreduce(void* buf, size_t count, bool f64, cudaStream_t stream);
+    // only_if (optional, device): same value on every rank; 0 = skip (consistently everywhere)
+    cudaError_t allreduce(void* buf, size_t count, bool f64, cudaStream_t stream, const int* only_if = nullptr);
 };
 }  // namespace lb
 

@@ -606,7 +606,14 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
         }
         // wait until the Cholesky kernel has published block-row jb of R
         if (tid == 0) {
-            while (ld_acquire(&fac->flag[jb]) == 0) { __nanosleep(64); }
+            // (invariant: the Cholesky grid raises flag[b] only after every write of block-row b, and writes
+            // nothing the apply reads after flag[3]; bounded, so that a protocol bug is a launch failure and
+            // not a hung GPU)
+            unsigned long long spins = 0;
+            while (ld_acquire(&fac->flag[jb]) == 0) {
+                __nanosleep(64);
+                if (++spins > (unsigned long long)(LB_SPIN_LIMIT)) __trap();
+            }
         }
         __syncthreads();   // also orders the previous stage's Q writes and Rb reads
         for (int e = tid; e < (jb + 1) * 256; e += APPLY_THREADS) {
@@ -785,8 +792,8 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
     const int rgrid = (GRAM_ELEMS + 31) / 32;
     const int* never = nullptr;
     // row-sharded factorisation: G becomes the Gram matrix of the global panel (sum over ranks)
-    auto global_sum = [&]() -> cudaError_t {
-        return comm ? comm->allreduce_f64(comm->self, G, GRAM_ELEMS, stream) : cudaSuccess;
+    auto global_sum = [&](const int* only_if = nullptr) -> cudaError_t {
+        return comm ? comm->allreduce_f64(comm->self, G, GRAM_ELEMS, stream, only_if) : cudaSuccess;
     };
 
     cudaError_t le;
@@ -807,9 +814,10 @@ cudaError_t panel_qr128(cudaStream_t stream, int num_sms, int m, float* A, long 
                              lda, m, part, redo)) != cudaSuccess) return le;
         if ((le = launch_pdl(gram128_reduce_kernel, dim3(rgrid), dim3(1024), 0, stream, (const double*)part,
                              ggrid, G, fac->flag, redo)) != cudaSuccess) return le;
-        // (unconditional - the launch sequence is static: when the panel was not redone this sums a stale G
-        // that the skipped Cholesky launch below never reads)
-        if ((le = global_sum()) != cudaSuccess) return le;
+        // (the launch sequence is static; the redo flag is the same on every rank, so the peer-memory
+        // kernel returns at once when the panel was not redone - NCCL would sum a stale G that the skipped
+        // Cholesky launch below never reads)
+        if ((le = global_sum(redo)) != cudaSuccess) return le;
         if ((le = launch_chol(stream, opts, G, R, ldr, fac, info, col0, 0, 0.0, redo)) != cudaSuccess) return le;
     } else {
         if ((le = launch_pdl(gram128_f64_kernel, dim3(ggrid), dim3(GRAM_THREADS), 0, stream, (const float*)A,

@@ -53,7 +53,9 @@ enum PanelInfo : int {
 // rank derives the same R from it.
 struct PanelComm {
     void* self;
-    cudaError_t (*allreduce_f64)(void* self, double* buf, size_t count, cudaStream_t stream);
+    // only_if (optional, device): a flag that holds the same value on every rank; when it reads 0 the
+    // collective may be skipped (the peer-memory kernel does; NCCL cannot and sums stale data nobody reads)
+    cudaError_t (*allreduce_f64)(void* self, double* buf, size_t count, cudaStream_t stream, const int* only_if);
 };
 
 // Scratch (bytes) needed by panel_qr128 for an m-row panel on a device with num_sms SMs.

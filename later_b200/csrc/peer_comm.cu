@@ -68,7 +68,7 @@ __host__ __device__ inline size_t seq_offset(size_t half_bytes) {
 
 template <typename T>
 __global__ void __launch_bounds__(kPeerThreads)
-peer_allreduce_kernel(T* __restrict__ data, size_t count, PeerTable t) {
+peer_allreduce_kernel(T* __restrict__ data, size_t count, PeerTable t, const int* __restrict__ only_if) {
     __shared__ int s_seq;
     const int c = blockIdx.x;
     uint8_t* mine = t.slab[t.rank];
@@ -76,6 +76,7 @@ peer_allreduce_kernel(T* __restrict__ data, size_t count, PeerTable t) {
     int* my_seq = reinterpret_cast<int*>(mine + seq_offset(t.half_bytes)) + c;
     pdl_trigger();
     pdl_wait();                               // `data` comes from the preceding kernel
+    if (only_if && *only_if == 0) return;     // (same decision on every rank: the counters stay in step)
     if (threadIdx.x == 0) s_seq = *my_seq + 1;   // per-CTA message counter, identical on every rank
     __syncthreads();
     const int seq = s_seq;
@@ -126,14 +127,14 @@ void PeerComm::release() {
 
 bool PeerComm::fits(size_t bytes) const { return ready && bytes <= half_bytes; }
 
-cudaError_t PeerComm::allreduce(void* buf, size_t count, bool f64, cudaStream_t stream) {
+cudaError_t PeerComm::allreduce(void* buf, size_t count, bool f64, cudaStream_t stream, const int* only_if) {
     PeerTable t{};
     for (int p = 0; p < nranks; ++p) t.slab[p] = static_cast<uint8_t*>(peers[p]);
     t.nranks = nranks; t.rank = rank; t.half_bytes = half_bytes;
     cudaError_t e = f64 ? launch_pdl(peer_allreduce_kernel<double>, dim3(kPeerCtas), dim3(kPeerThreads), 0, stream,
-                                     static_cast<double*>(buf), count, t)
+                                     static_cast<double*>(buf), count, t, only_if)
                         : launch_pdl(peer_allreduce_kernel<float>, dim3(kPeerCtas), dim3(kPeerThreads), 0, stream,
-                                     static_cast<float*>(buf), count, t);
+                                     static_cast<float*>(buf), count, t, only_if);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -212,11 +212,13 @@ __global__ void finish_r12_kernel(const float* __restrict__ S, int h, int nb, fl
     }
 }
 
-cudaError_t comm_allreduce(later_b200_ctx* ctx, void* buf, size_t count, int dtype, cudaStream_t stream) {
+cudaError_t comm_allreduce(later_b200_ctx* ctx, void* buf, size_t count, int dtype, cudaStream_t stream,
+                           const int* only_if = nullptr) {
     // small blocks (everything this factorisation exchanges unless n is huge): one launch of the NVLink
     // peer-memory kernel (peer_comm.cu), ~5 us; NCCL (~33 us per call at 8 GPUs) for the rest
     const size_t bytes = count * (dtype == kNcclDouble ? sizeof(double) : sizeof(float));
-    if (ctx->peer.fits(bytes) && ctx->opts.peer_allreduce) return ctx->peer.allreduce(buf, count, dtype == kNcclDouble, stream);
+    if (ctx->peer.fits(bytes) && ctx->opts.peer_allreduce)
+        return ctx->peer.allreduce(buf, count, dtype == kNcclDouble, stream, only_if);
     if (!ctx->comm || !ctx->nccl) return cudaErrorNotReady;
     const ncclResult_t r = ctx->comm_group
         ? ctx->comm_group->allreduce(ctx->nccl, ctx->rank, buf, count, dtype, ctx->comm, stream)
@@ -228,8 +230,8 @@ cudaError_t comm_allreduce(later_b200_ctx* ctx, void* buf, size_t count, int dty
     }
     return cudaSuccess;
 }
-cudaError_t comm_allreduce_f64(void* self, double* buf, size_t count, cudaStream_t stream) {
-    return comm_allreduce(static_cast<later_b200_ctx*>(self), buf, count, kNcclDouble, stream);
+cudaError_t comm_allreduce_f64(void* self, double* buf, size_t count, cudaStream_t stream, const int* only_if) {
+    return comm_allreduce(static_cast<later_b200_ctx*>(self), buf, count, kNcclDouble, stream, only_if);
 }
 
 struct Recursion {

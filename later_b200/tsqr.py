@@ -20,6 +20,9 @@ import torch
 import torch.distributed as dist
 
 
+_default_ctxs: dict = {}
+
+
 def stack_from_gathered(gathered_t: torch.Tensor) -> torch.Tensor:
     """gathered_t[p] holds R_p^T row-major (= R_p column-major), shape (P, n, n).  Returns the
     column-major (P*n) x n stack [R_0; R_1; ...] as a tensor of shape (P*n, n), strides (1, P*n)."""
@@ -45,8 +48,11 @@ def tsqr_rgsqrf(m_local: int, n: int, A: torch.Tensor, lda: int, R: torch.Tensor
         raise ValueError("host_A needs the built-in local_qr")
     if local_qr is None:
         from . import qr as _qr
-        if ctxs is None:
-            ctxs = (_qr.Context(), _qr.Context())
+        if ctxs is None:                      # one pair per device, kept: graphs and workspaces are reused
+            dev = torch.cuda.current_device()
+            if dev not in _default_ctxs:
+                _default_ctxs[dev] = (_qr.Context(dev), _qr.Context(dev))
+            ctxs = _default_ctxs[dev]
         main_ctx, stack_ctx = ctxs
 
         def local_qr(m, n_, a, lda_, r, ldr_):

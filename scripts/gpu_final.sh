@@ -8,10 +8,10 @@ mkdir -p $O
 timeout 600 python -m pytest tests -m gpu -q -rf --no-header > $O/r02_tests.log 2>&1; echo "tests rc=$?"; tail -3 $O/r02_tests.log
 timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > $O/r02_bench_ref.json 2> $O/r02_bench_ref.err; echo "bench ref rc=$?"
 timeout 300 python bench.py --steps 10 --warmup 3 > $O/r02_bench_b200.json 2> $O/r02_bench_b200.err; echo "bench rc=$?"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r02_launches_bench.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1100 --csv --log-file $O/r02_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs --no-e2e > $O/r02_bench_under_ncu.log 2>&1; echo "ncu bench rc=$?"
 cap() {  # name regex count m n
-  timeout 240 ncu --set full --clock-control none --import-source on -k "regex:$2" -c $3 -f -o $O/prof_$1 \
+  timeout 240 ncu --set full --clock-control none -k "regex:$2" -c $3 -f -o $O/prof_$1 \
       python scripts/gpu_profile_run.py $4 $5 1 > $O/prof_$1.log 2>&1; echo "ncu $1 rc=$?"
 }
 cap gram16k 'tc_gemm_kernel<256, *false, *0>|tc_gemm_kernelILi256ELb0ELi0' 5 16384 16384
