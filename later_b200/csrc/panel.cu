@@ -6,7 +6,7 @@
 //   chol128b_kernel       R = chol(G) in fp64 on one CTA, blocked by 32 columns: one warp factors each
 //                         diagonal block (two columns per step), the others solve, update (fp64
 //                         tensor path) and publish R block-row by block-row; barriers only
-//   apply128_kernel       Q = A R^-1 by forward substitution, four threads per matrix row; launched
+//   apply128_kernel       Q = A R^-1 by forward substitution, right-looking, two threads per matrix row; launched
 //                         with programmatic dependent launch so that it runs CONCURRENTLY with the
 //                         Cholesky kernel and consumes each 32-row block of R as soon as its flag is
 //                         raised; writes Q (fp32, in place) and its fp16 shadow
@@ -544,18 +544,21 @@ chol128b_kernel(const double* __restrict__ G, float* __restrict__ R, long ldr, P
 }
 
 // ---------------------------------------------------------------------------------------------
-// Q = A R^-1.  128 rows per CTA, 128 threads: thread (rg, p) owns a 4-row x 8-column register tile -
-// rows 4 rg .. 4 rg + 3 and the columns c = p (mod 4) of the current 32-column block - so every
-// shared-memory operand it loads (4 q values, 8 R values, both as 16-byte loads) feeds 32 FMAs.
-// Per block jb: wait for block-row jb of R (flag raised by the Cholesky kernel, which is still
-// running), project out the earlier blocks (a_jb -= q_ib R(ib, jb)), then forward substitution
-// against the diagonal block, the owner of column k broadcasting q_k to the three other parts.
+// Q = A R^-1, right-looking.  128 rows per CTA, 256 threads: thread (rg, p) owns rows 2 rg, 2 rg + 1 and,
+// in each of the four 32-column blocks, the columns c = p (mod 4) - the whole 2 x 32 share of the panel
+// lives in registers from the first stage to the last.  Stage jb waits for block-row jb of R (flag raised
+// by the Cholesky kernel, which is still running), turns block jb into Q by forward substitution against
+// the diagonal block (the owner of column k broadcasting q_k to the three other parts of its quad), writes
+// it out, and projects it out of the blocks to its right at once (a_j -= q_jb R(jb, j), j > jb).  When the
+// last flag goes up only the 32 x 32 substitution of block 3 is left - the Cholesky kernel is the critical
+// path of the panel and this is what it is followed by.  Every accumulator sees the same fused
+// multiply-adds in the same order as in a left-looking sweep (blocks ascending, k ascending).
 constexpr int APPLY_ROWS = 128;
-constexpr int APPLY_THREADS = APPLY_ROWS;        // (APPLY_ROWS / 4) row groups x 4 column parts
-constexpr int APPLY_LDQ = APPLY_ROWS + 8;        // 136 floats: parts p = 0..3 land 8 banks apart
+constexpr int APPLY_THREADS = 2 * APPLY_ROWS;    // (APPLY_ROWS / 2) row pairs x 4 column parts
+constexpr int APPLY_LDQ = APPLY_ROWS + 16;       // 144 floats: parts p = 0..3 land 16 banks apart
 struct ApplySmem {
-    float Q[96][APPLY_LDQ];    // finished blocks 0..2 of the row block (for the projections)
-    float Rb[4][32][32];       // R(0..jb-1, jb) blocks of the current stage, [3] = diagonal block
+    float Q[32][APPLY_LDQ];    // the block just finished (each quad reads back only its own rows)
+    float Rb[4][32][32];       // block-row jb of R: [0] = diagonal block, [d] = R(jb, jb + d); [k][perm(c)]
     float rinv[32];
 };
 
@@ -565,19 +568,39 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(APPLY_THREADS, 3)
+// acc[d] -= q R(jb, jb + d) for the ND blocks to the right of the one just finished
+template <int ND>
+__device__ __forceinline__ void apply_project(float (&acc)[4][2][8], const ApplySmem& s, int rg, int p) {
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+        const float2 qv = *reinterpret_cast<const float2*>(&s.Q[k][2 * rg]);
+#pragma unroll
+        for (int d = 1; d <= ND; ++d) {
+            const float4 ra = *reinterpret_cast<const float4*>(&s.Rb[d][k][p * 8]);
+            const float4 rb = *reinterpret_cast<const float4*>(&s.Rb[d][k][p * 8 + 4]);
+            const float rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                acc[d][0][q] = fmaf(-qv.x, rr[q], acc[d][0][q]);
+                acc[d][1][q] = fmaf(-qv.y, rr[q], acc[d][1][q]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(APPLY_THREADS, 2)
 apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __restrict__ fac,
                 __half* __restrict__ Qh, long ldqh, const int* __restrict__ only_if) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     ApplySmem& s = *reinterpret_cast<ApplySmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int rg = tid >> 2, p = tid & 3;    // row group (rows 4 rg ..), column part
+    const int rg = tid >> 2, p = tid & 3;    // row pair, column part
     const int lane = tid & 31;
-    const int grow = blockIdx.x * APPLY_ROWS + 4 * rg;   // first global row of this thread's tile
-    const int nvalid = min(4, max(0, m - grow));         // rows of this tile inside the matrix
-    const bool rows_ok = nvalid == 4;
-    const bool vec_a = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    const bool vec_h = Qh && (ldqh % 4 == 0) && ((reinterpret_cast<uintptr_t>(Qh) & 7) == 0);
+    const int grow = blockIdx.x * APPLY_ROWS + 2 * rg;   // first global row of this thread
+    const int nvalid = min(2, max(0, m - grow));         // rows of this thread inside the matrix
+    const bool rows_ok = nvalid == 2;
+    const bool vec_a = (lda % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 7) == 0);
+    const bool vec_h = Qh && (ldqh % 2 == 0) && ((reinterpret_cast<uintptr_t>(Qh) & 3) == 0);
     pdl_trigger();   // (no pdl_wait: this grid synchronises with the Cholesky grid through flags)
     if (only_if) {   // conditional launch behind the tensor-core apply of a tall panel: runs iff the panel
                      // was factored again from the fp64 Gram matrix (every flag has long been raised)
@@ -585,25 +608,10 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
         if (*only_if == 0) return;
     }
 
+    // acc[0] is always the block being finished, acc[1..] the blocks to its right
+    float acc[4][2][8];                          // [block][row][q]: column 4 q + p of the block
 #pragma unroll 1
     for (int jb = 0; jb < 4; ++jb) {
-        // this thread's 4 x 8 tile of block jb straight from global memory (a warp touches four
-        // columns x 128 contiguous bytes per request); issued before the wait so it overlaps it
-        float acc[4][8];                         // [row][q]: column 4 q + p of block jb
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float* src = A + grow + (long)(jb * 32 + 4 * q + p) * lda;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rows_ok && vec_a) {
-                v = *reinterpret_cast<const float4*>(src);
-            } else {
-                if (nvalid > 0) v.x = src[0];
-                if (nvalid > 1) v.y = src[1];
-                if (nvalid > 2) v.z = src[2];
-                if (nvalid > 3) v.w = src[3];
-            }
-            acc[0][q] = v.x; acc[1][q] = v.y; acc[2][q] = v.z; acc[3][q] = v.w;
-        }
         // wait until the Cholesky kernel has published block-row jb of R
         if (tid == 0) {
             // (invariant: the Cholesky grid raises flag[b] only after every write of block-row b, and writes
@@ -615,48 +623,35 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
                 if (++spins > (unsigned long long)(LB_SPIN_LIMIT)) __trap();
             }
         }
-        __syncthreads();   // also orders the previous stage's Q writes and Rb reads
-        for (int e = tid; e < (jb + 1) * 256; e += APPLY_THREADS) {
-            const int b = e >> 8, w4 = e & 255;           // block, float4 index inside it
+        __syncthreads();   // also: everybody has finished reading the previous stage's Rb
+        if (jb == 0) {
+            // The panel itself is read only now, behind the first flag: the Cholesky kernel has waited for
+            // the whole chain of kernels before it (Gram <- update), this grid has not.  A warp touches four
+            // columns x 64 contiguous bytes per request.
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float* src = A + grow + (long)(b * 32 + 4 * q + p) * lda;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (rows_ok && vec_a) {
+                        v = *reinterpret_cast<const float2*>(src);
+                    } else {
+                        if (nvalid > 0) v.x = src[0];
+                        if (nvalid > 1) v.y = src[1];
+                    }
+                    acc[b][0][q] = v.x; acc[b][1][q] = v.y;
+                }
+        }
+        for (int e = tid; e < (4 - jb) * 256; e += APPLY_THREADS) {
+            const int d = e >> 8, w4 = e & 255;           // block jb + d of the block-row, float4 index inside it
             const float4* src = reinterpret_cast<const float4*>(
-                b < jb ? &fac->Roff[off_index(b, jb)][0][0] : &fac->Rdiag[jb][0][0]);
-            reinterpret_cast<float4*>(&s.Rb[b < jb ? b : 3][0][0])[w4] = __ldcg(src + w4);
+                d == 0 ? &fac->Rdiag[jb][0][0] : &fac->Roff[off_index(jb, jb + d)][0][0]);
+            reinterpret_cast<float4*>(&s.Rb[d][0][0])[w4] = __ldcg(src + w4);
         }
         if (tid < 32) s.rinv[tid] = __ldcg(&fac->rinv[jb * 32 + tid]);
         __syncthreads();
 
-        // project out the finished blocks, software-pipelined over groups of 4 k-steps
-        {
-            const int T = jb * 8;                // groups of 4 consecutive k over all ib < jb
-            float4 qn[4], ran[4], rbn[4];
-            auto load_group = [&](int it) {
-                const int ib = it >> 3, k0 = (it & 7) << 2;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    qn[u] = *reinterpret_cast<const float4*>(&s.Q[ib * 32 + k0 + u][4 * rg]);
-                    ran[u] = *reinterpret_cast<const float4*>(&s.Rb[ib][k0 + u][p * 8]);
-                    rbn[u] = *reinterpret_cast<const float4*>(&s.Rb[ib][k0 + u][p * 8 + 4]);
-                }
-            };
-            if (T > 0) load_group(0);
-#pragma unroll 1
-            for (int it = 0; it < T; ++it) {
-                float4 qv[4], ra[4], rb[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { qv[u] = qn[u]; ra[u] = ran[u]; rb[u] = rbn[u]; }
-                if (it + 1 < T) load_group(it + 1);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float qq[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
-                    const float rr[8] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w,
-                                         rb[u].x, rb[u].y, rb[u].z, rb[u].w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) acc[i][q] = fmaf(-qq[i], rr[q], acc[i][q]);
-                }
-            }
-        }
         // forward substitution against the diagonal block; column k = 4 kq + kp is owned by part kp
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq) {
@@ -664,8 +659,8 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
             float rv[4];
 #pragma unroll
             for (int kp = 0; kp < 4; ++kp) {
-                da[kp] = *reinterpret_cast<const float4*>(&s.Rb[3][4 * kq + kp][p * 8]);
-                db[kp] = *reinterpret_cast<const float4*>(&s.Rb[3][4 * kq + kp][p * 8 + 4]);
+                da[kp] = *reinterpret_cast<const float4*>(&s.Rb[0][4 * kq + kp][p * 8]);
+                db[kp] = *reinterpret_cast<const float4*>(&s.Rb[0][4 * kq + kp][p * 8 + 4]);
                 rv[kp] = s.rinv[4 * kq + kp];
             }
 #pragma unroll
@@ -673,46 +668,47 @@ apply128_kernel(float* __restrict__ A, long lda, int m, const PanelFactors* __re
                 const float rr[8] = {da[kp].x, da[kp].y, da[kp].z, da[kp].w,
                                      db[kp].x, db[kp].y, db[kp].z, db[kp].w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float qk = acc[i][kq] * rv[kp];
+                for (int i = 0; i < 2; ++i) {
+                    float qk = acc[0][i][kq] * rv[kp];
                     qk = __shfl_sync(0xffffffffu, qk, (lane & ~3) | kp);
-                    if (p == kp) acc[i][kq] = qk;
+                    if (p == kp) acc[0][i][kq] = qk;
 #pragma unroll
                     for (int q = kq; q < 8; ++q) {
                         // column 4 q + p is updated iff it lies to the right of column 4 kq + kp
-                        if (q > kq || p > kp) acc[i][q] = fmaf(-qk, rr[q], acc[i][q]);
+                        if (q > kq || p > kp) acc[0][i][q] = fmaf(-qk, rr[q], acc[0][i][q]);
                     }
                 }
             }
         }
-        // finished block: to global (fp32 in place + fp16 shadow) and, for the later projections,
-        // to shared memory
+        // finished block: to global (fp32 in place + fp16 shadow) and, for the projections, to shared memory
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int c = jb * 32 + 4 * q + p;
-            const float4 v = make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
-            if (jb < 3) *reinterpret_cast<float4*>(&s.Q[c][4 * rg]) = v;
+            const float2 v = make_float2(acc[0][0][q], acc[0][1][q]);
+            if (jb < 3) *reinterpret_cast<float2*>(&s.Q[4 * q + p][2 * rg]) = v;
             if (nvalid > 0) {
                 float* dst = A + grow + (long)c * lda;
-                const float vv[4] = {v.x, v.y, v.z, v.w};
-                if (rows_ok && vec_a) *reinterpret_cast<float4*>(dst) = v;
-                else for (int i = 0; i < nvalid; ++i) dst[i] = vv[i];
+                if (rows_ok && vec_a) *reinterpret_cast<float2*>(dst) = v;
+                else { dst[0] = v.x; if (nvalid > 1) dst[1] = v.y; }
                 if (Qh) {
                     __half* hd = Qh + grow + (long)c * ldqh;
-                    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-                    if (rows_ok && vec_h) {
-                        uint2 pk;
-                        pk.x = *reinterpret_cast<const uint32_t*>(&h01);
-                        pk.y = *reinterpret_cast<const uint32_t*>(&h23);
-                        *reinterpret_cast<uint2*>(hd) = pk;
-                    } else {
-                        const __half hh[4] = {__low2half(h01), __high2half(h01), __low2half(h23),
-                                              __high2half(h23)};
-                        for (int i = 0; i < nvalid; ++i) hd[i] = hh[i];
-                    }
+                    const __half2 h01 = __floats2half2_rn(v.x, v.y);
+                    if (rows_ok && vec_h) *reinterpret_cast<__half2*>(hd) = h01;
+                    else { hd[0] = __low2half(h01); if (nvalid > 1) hd[1] = __high2half(h01); }
                 }
             }
         }
+        if (jb == 3) break;
+        __syncwarp();      // the four parts of a row pair sit in one warp
+        if (jb == 0) apply_project<3>(acc, s, rg, p);
+        else if (jb == 1) apply_project<2>(acc, s, rg, p);
+        else apply_project<1>(acc, s, rg, p);
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[b][i][q] = acc[b + 1][i][q];
     }
 }
 

@@ -96,7 +96,8 @@ Workspace plan_workspace(int num_sms, int m, int n, bool dist = false) {
     w.r12h_bytes = n > NMIN ? (size_t)(n / 2) * (n / 2) * sizeof(__half) : 0;
     size_t part = 0;
     for (int h = NMIN; h * 2 <= n; h *= 2) {
-        const int s = choose_gram_splits(num_sms, h, h, gram_bn(h), m);
+        int s = choose_gram_splits(num_sms, h, h, gram_bn(h), m);
+        if (s > 1 && tc_gram_cast_supports(h)) s = std::max(s, tc_gram_cast_splits(num_sms, h, m));
         if (s > 1) part = std::max(part, (size_t)s * h * h * sizeof(float));
     }
     w.part_bytes = part;
@@ -280,11 +281,17 @@ struct Recursion {
     // b_is_input: A2 is still the caller's fp32 input - no kernel has written its fp16 shadow yet.
     // Tall (bandwidth-bound) products then round it to fp16 inside the Gram kernel's load path
     // (tc_gram_cast.cu); otherwise the shadow is made first.
-    void gram_update(int c0, int h, int cb, int nb, bool zero_mirror, bool b_is_input) {
+    // panel_next: columns cb .. cb + 127 are factored next (their fp16 shadow would never be read).
+    void gram_update(int c0, int h, int cb, int nb, bool zero_mirror, bool b_is_input, bool panel_next) {
         if (err != cudaSuccess) return;
         cudaStream_t st = ctx->stream;
         const int bn = nb % 256 == 0 ? gram_bn(h) : 128;
-        const int splits = choose_gram_splits(ctx->num_sms, h, h, gram_bn(h), p->m);
+        // Tall nodes on the left spine take the split-K factor of the cast-fused kernel (one that fills the SMs
+        // with its Mc x 128 strips) whether or not that kernel is enabled: the factor fixes the summation order.
+        const int generic = choose_gram_splits(ctx->num_sms, h, h, gram_bn(h), p->m);
+        const bool cast_node = b_is_input && generic >= 2 && tc_gram_cast_supports(h) && p->m >= kTcApplyMinRows &&
+                               p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->A) & 15) == 0;
+        const int splits = cast_node ? tc_gram_cast_splits(ctx->num_sms, h, p->m) : generic;
         float* R12 = p->R + c0 + (long)cb * p->ldr;
         // (the mirror block R21, which the algorithm never produces, is written as zero on the way)
         float* Z = zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr;
@@ -295,9 +302,7 @@ struct Recursion {
         const long ldc = p->dist ? h : p->ldr;
         __half* Ch = p->dist ? nullptr : p->R12h;
         float* Zk = p->dist ? nullptr : Z;
-        const bool fused = b_is_input && ctx->opts.gram_cast && splits >= 2 && tc_gram_cast_supports(h) &&
-                           p->m >= kTcApplyMinRows && p->lda % 4 == 0 &&
-                           (reinterpret_cast<uintptr_t>(p->A) & 15) == 0;
+        const bool fused = cast_node && ctx->opts.gram_cast;
         if (fused) {
             check(tc_gram_cast(st, ctx->num_sms, q128, p->m, c0, h, p->A + (long)cb * p->lda, p->lda, nb,
                                C, ldc, Ch, h, p->part, splits, Zk));
@@ -329,7 +334,7 @@ struct Recursion {
             check(tc_update_tma(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, nb, p->A, p->m,
                                 p->n, p->lda, cb, p->Qh, p->ldh, true,
                                 want ? panel_colmax_scratch(p->panel_scratch, p->m, ctx->num_sms) : nullptr,
-                                kColmaxParts));
+                                kColmaxParts, panel_next ? NMIN : 0));
             if (want) colmax_col = cb;
         } else {   // (TMA also needs 16-byte aligned column strides)
             check(tc_update(st, ctx->num_sms, q64, r12map, ubn, 0, p->m, c0, h, 0, nb,
@@ -347,10 +352,13 @@ struct Recursion {
             // (piece 0 is cast by the left spine of its own recursion; a later piece is the caller's
             // input until the first - widest - of these updates has run)
             bool fresh = j > 0;
+            int last = 0;                           // the narrowest node that updates this piece
+            for (int s = pieces; s >= 2; s /= 2)
+                if (j - j / s * s >= s / 2) last = s;
             for (int s = pieces; s >= 2; s /= 2) {
                 const int a = j / s * s;            // node (a, s) in pieces; j in its right half?
                 if (j - a >= s / 2) {
-                    gram_update(a * P, s / 2 * P, cj, P, false, fresh);
+                    gram_update(a * P, s / 2 * P, cj, P, false, fresh, s == last);
                     fresh = false;
                 }
             }
@@ -370,7 +378,7 @@ struct Recursion {
         const int h = w / 2;
         // Left spine (c0 == 0): A2 is still the caller's input; everywhere else the update that last
         // wrote A2 has refreshed its fp16 shadow.
-        gram_update(c0, h, c0 + h, h, true, c0 == 0);
+        gram_update(c0, h, c0 + h, h, true, c0 == 0, true);
         qr(c0 + h, h);
     }
 };
@@ -899,7 +907,7 @@ int later_b200_oc_qr(later_b200_ctx* ctx, int m, int n, float* hA, int lda, floa
             }
             ck(cudaStreamWaitEvent(st, ev_in[slot], 0));
             rec.cast(slot * B, slot * B + B);                        // fp16 operand of the two products
-            rec.gram_update(slot * B, B, 2 * B, B, false, i == 0);   // R_ij, A_j -= Q_i R_ij
+            rec.gram_update(slot * B, B, 2 * B, B, false, i == 0, i + 1 == j);   // R_ij, A_j -= Q_i R_ij
             ck(cudaEventRecord(ev_free[slot], st));
             // R_ij -> host (ordered behind the products on the main stream; B x B, small)
             ck(cudaMemcpy2DAsync(hR + (size_t)i * B + (size_t)j * B * ldr, (size_t)ldr * sizeof(float),

@@ -100,6 +100,9 @@ cudaError_t tc_gram_cast(cudaStream_t stream, int num_sms, const CUtensorMap& ma
                          int colA, int Mc, const float* B, long ldb, int Nc, float* C, long ldc, __half* Ch,
                          long ldch, float* part, int splits, float* Z);
 bool tc_gram_cast_supports(int Mc);
+// split-K factor of the cast-fused product for a node of half-width Mc (its CTAs own Mc x 128 output
+// strips, so the generic choose_gram_splits, which counts 128 x bn tiles, would fill half the SMs)
+int tc_gram_cast_splits(int num_sms, int Mc, int k_rows);
 cudaError_t tc_gram_cast_init();
 
 // Sets the dynamic shared-memory limits of all kernel instantiations (once per device).
@@ -112,10 +115,12 @@ cudaError_t tc_update_init();
 // shadow of the new C block goes to the same coordinates of Hmat (ld ldh).  Nc must be a multiple
 // of bn unless the block ends at the matrix edge.  colmax_part (sub only, optional): per-CTA partial
 // maxima of |new C| over the block's first 128 columns, [col][colmax_parts] floats, every slot written.
+// shadow_from (sub only, a multiple of 32): the shadow of the block's first shadow_from columns is not
+// written - for columns whose shadow the next panel's apply kernel rewrites before anybody reads it.
 cudaError_t tc_update_tma(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_64,
                           const CUtensorMap& mapB_bn, int bn, int row0, int Mr, int colA, int K,
                           int colB0, int Nc, float* Cmat, long c_rows, long c_cols, long ldc, int c_c0,
                           __half* Hmat, long ldh, bool sub, float* colmax_part = nullptr,
-                          int colmax_parts = 0);
+                          int colmax_parts = 0, int shadow_from = 0);
 
 }  // namespace lb

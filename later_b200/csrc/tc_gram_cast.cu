@@ -286,6 +286,14 @@ cudaError_t tc_gram_cast_init() {
 
 bool tc_gram_cast_supports(int Mc) { return Mc == 128 || Mc == 256 || Mc == 512; }
 
+int tc_gram_cast_splits(int num_sms, int Mc, int k_rows) {
+    const int strips = (Mc + BN - 1) / BN;                 // of the whole node: Nc = Mc
+    const int kb_total = (k_rows + BK - 1) / BK;
+    int s = std::max(2, std::min(num_sms / strips, kb_total / 8));      // one wave, >= 8 k blocks per split
+    const int kb_per = (kb_total + s - 1) / s;
+    return std::max(1, (kb_total + kb_per - 1) / kb_per);  // no empty split
+}
+
 cudaError_t tc_gram_cast(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int k_rows,
                          int colA, int Mc, const float* B, long ldb, int Nc, float* C, long ldc, __half* Ch,
                          long ldch, float* part, int splits, float* Z) {

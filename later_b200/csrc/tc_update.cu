@@ -54,6 +54,9 @@ struct UpdParams {
     // These columns are the next panel; its integer Gram kernel scales by them (panel_tc.cu).
     float* colmax_part;
     int colmax_parts;
+    // The fp16 shadow of the first shadow_from columns of the block is not written: those columns are the
+    // next panel, whose apply kernel rewrites their shadow before anybody reads it (a multiple of CCH).
+    int shadow_from;
 };
 
 __device__ __forceinline__ void tile_coords_u(int t, int tiles_m, int tiles_n, int& m_blk,
@@ -230,12 +233,13 @@ tc_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
                 tmem_ld_wait();
                 const bool track = p.colmax_part && n_blk == 0 && c * CCH < 128;   // warp-uniform
+                const bool shadow = SHADOW && n_blk * BN + c * CCH >= p.shadow_from;
 #pragma unroll
                 for (int j = 0; j < CCH; ++j) {
                     const float dv = __uint_as_float(d[j]);
                     const float v = SUB ? sc[j * BM + r] - dv : dv;
                     sc[j * BM + r] = v;
-                    if (SHADOW) sh[j * BM + r] = __float2half_rn(v);
+                    if (shadow) sh[j * BM + r] = __float2half_rn(v);
                     if (track) d[j] = __float_as_uint(fabsf(v));   // (ordered like unsigned integers)
                 }
                 if (track) {
@@ -260,7 +264,7 @@ tc_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     const int row0 = p.c_r0 + m_blk * BM;
                     const int col0 = p.c_c0 + n_blk * BN + c * CCH;
                     tma_store_2d(&mapC, cring_base + slot * C::CSLOT_BYTES, row0, col0);
-                    if (SHADOW)
+                    if (shadow)
                         tma_store_2d(&mapH, cring_base + slot * C::CSLOT_BYTES + C::C32_BYTES, row0, col0);
                     tma_store_commit();
                     if (SUB && pending_slot >= 0) {
@@ -365,8 +369,10 @@ cudaError_t tc_update_init() {
 cudaError_t tc_update_tma(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_64,
                           const CUtensorMap& mapB_bn, int bn, int row0, int Mr, int colA, int K,
                           int colB0, int Nc, float* Cmat, long c_rows, long c_cols, long ldc, int c_c0,
-                          __half* Hmat, long ldh, bool sub, float* colmax_part, int colmax_parts) {
+                          __half* Hmat, long ldh, bool sub, float* colmax_part, int colmax_parts,
+                          int shadow_from) {
     UpdParams p{};
+    p.shadow_from = sub ? shadow_from : 0;
     p.colmax_part = sub ? colmax_part : nullptr;
     p.colmax_parts = colmax_parts;
     p.M = Mr; p.N = Nc;
