@@ -100,6 +100,7 @@ Workspace plan_workspace(int num_sms, int m, int n, bool dist = false) {
         if (s > 1 && tc_gram_cast_supports(h)) s = std::max(s, tc_gram_cast_splits(num_sms, h, m));
         if (s > 1) part = std::max(part, (size_t)s * h * h * sizeof(float));
     }
+    if (n > NMIN && tc_node128_supports(num_sms, m)) part = std::max(part, tc_node128_part_floats(m) * sizeof(float));
     w.part_bytes = part;
     w.panel_bytes = panel_scratch_bytes(m, num_sms);
     w.wh_bytes = (size_t)n * n * sizeof(__half);  // fp16 W of the TSQR back-multiplication
@@ -285,6 +286,20 @@ struct Recursion {
     void gram_update(int c0, int h, int cb, int nb, bool zero_mirror, bool b_is_input, bool panel_next) {
         if (err != cudaSuccess) return;
         cudaStream_t st = ctx->stream;
+        // A 128-column node whose right half is factored next, on a matrix short enough for one CTA per
+        // 128-row tile: Gram product, reduce and update in one launch (tc_node128, tc_update.cu).
+        if (ctx->opts.node_fuse && h == NMIN && nb == NMIN && panel_next && !p->dist &&
+            tc_node128_supports(ctx->num_sms, p->m) && p->lda % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
+            if (b_is_input) cast(cb, cb + nb);
+            check(tc_node128(st, ctx->num_sms, q128, p->m, c0, cb, p->A, p->n, p->lda,
+                             p->R + c0 + (long)cb * p->ldr, p->ldr,
+                             zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr, p->R12h, p->part,
+                             ctx->d_info + kInfoWords));
+            launches += 1;
+            colmax_col = -1;
+            return;
+        }
         const int bn = nb % 256 == 0 ? gram_bn(h) : 128;
         // Tall nodes on the left spine take the split-K factor of the cast-fused kernel (one that fills the SMs
         // with its Mc x 128 strips) whether or not that kernel is enabled: the factor fixes the summation order.
@@ -575,6 +590,7 @@ void read_options(Options& o) {
     o.ormqr_kchunk = std::max(64, geti("LB_ORMQR_KCHUNK", 2048) / 64 * 64);
     o.gram_2cta = geti("LB_GRAM_2CTA", 1) != 0;
     o.peer_allreduce = geti("LB_PEER_ALLREDUCE", 1) != 0;
+    o.node_fuse = geti("LB_NODE_FUSE", 1) != 0;
 }
 
 std::string rank_message(const int* info) {
@@ -624,15 +640,16 @@ int later_b200_create(later_b200_ctx** out, int device, void* stream) {
     ctx->stream = static_cast<cudaStream_t>(stream);
     ctx->arena.bind(ctx->stream);
     read_options(ctx->opts);
-    cudaError_t e = cudaMalloc(&ctx->d_info, kInfoWords * sizeof(int));
+    cudaError_t e = cudaMalloc(&ctx->d_info, (kInfoWords + kSyncWords) * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_info, kInfoWords * sizeof(int));
     if (e == cudaSuccess) {
         memset(ctx->h_info, 0, kInfoWords * sizeof(int));
-        e = cudaMemset(ctx->d_info, 0, kInfoWords * sizeof(int));
+        e = cudaMemset(ctx->d_info, 0, (kInfoWords + kSyncWords) * sizeof(int));
     }
     if (e == cudaSuccess) e = tc_gemm_init();
     if (e == cudaSuccess) e = tc_gram_cast_init();
     if (e == cudaSuccess) e = tc_update_init();
+    if (e == cudaSuccess) e = tc_node128_init();
     if (e == cudaSuccess) e = panel_init();
     if (e != cudaSuccess) {
         int rc = cuda_fail(ctx, e, "context setup");

@@ -336,6 +336,211 @@ cudaError_t make_plain_map(CUtensorMap* out, const void* ptr, int elem_bytes, lo
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// ---------------------------------------------------------------------------------------------
+// A whole 128-column node of the recursion in ONE launch, for matrices of at most 128 x #SMs rows:
+//     R12 = Q1^T A2 (128 x 128),   A2 -= Q1 R12        (Q1, A2: m x 128)
+// Separately this is a split-K Gram kernel, its reduce kernel and an update kernel - three launches with
+// a few microseconds of work each (16384 rows: 12 + 5 + 22 us under ncu for 3 us of memory time), 64 times
+// per 16384 x 16384 factorisation.  Here CTA t owns rows 128 t .. 128 t + 127 from start to end:
+//   1. TMA: its Q1 tile and the fp16 shadow of its A2 tile (K-major, 2 k blocks), and - running ahead - its
+//      fp32 A2 tile; tcgen05.mma -> partial Gram block in TMEM -> global partial t (fp32, 64 KB)
+//   2. grid barrier; the CTAs share the fixed-order sum over the partials (t = 0, 1, ...: deterministic), CTA c
+//      taking outputs [c per, (c + 1) per): R12 to R (fp32), its zero mirror block, and the fp16 operand
+//   3. grid barrier; every CTA stages the fp16 R12 (32 KB) as the K-major B operand, and multiplies the Q1
+//      tile STILL IN SHARED MEMORY by it (the K-major tile of the Gram product is, byte for byte, the
+//      MN-major A operand of the update: one 128-byte row per matrix column); epilogue A2 - D in the staged
+//      fp32 tile, TMA store.  No fp16 shadow of the new A2: the node's right half is the next panel.
+// The grid barriers are counters in global memory (self-resetting: the last CTA to leave clears them); all
+// CTAs are co-resident because the grid is at most one CTA per SM and nothing before it in the stream waits
+// for it.  Spins are bounded (trap), like every other wait in this library.
+constexpr int NODE_THREADS = 192;
+constexpr int NODE_TILE = 128 * 128;                       // outputs of the node = floats per partial
+constexpr int NODE_SMEM_BYTES = 2 * A_TILE_BYTES /*Q1*/ + 2 * A_TILE_BYTES /*A2h, then R12h*/ +
+                                BM * 128 * 4 /*fp32 A2 tile*/ + 256 + 1024;
+
+struct NodeParams {
+    int tiles;             // row tiles = gridDim.x
+    int q_c1, b_c1;        // first column of Q1 / of A2 (shadow and matrix coordinates)
+    float* part;           // [tiles][128 n][128 m]
+    float* R12; long ldr;  // R12 block inside R
+    float* Z;              // mirror block to clear (same ld) or null
+    __half* R12h;          // fp16 R12, ld 128
+    int* sync;             // three zero-initialised counters
+};
+
+__device__ __forceinline__ void node_grid_barrier(int* counter, int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // this CTA's global writes before the arrival
+        atomicAdd(counter, 1);
+        unsigned long long spins = 0;
+        int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (++spins > (unsigned long long)(LB_SPIN_LIMIT)) __trap();
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NODE_THREADS, 1)
+tc_node128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapC,
+                  const NodeParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t sQ = smem_base;                         // Q1 tile: 2 k blocks x [128 columns][64 rows] fp16
+    const uint32_t sB = sQ + 2 * A_TILE_BYTES;             // A2 shadow tile, later R12h: same shape
+    const uint32_t sC = sB + 2 * A_TILE_BYTES;             // fp32 A2 tile: 4 chunks x [32 columns][128 rows]
+    const uint32_t bar_base = sC + BM * 128 * 4;
+    const uint32_t bar_in = bar_base, bar_c = bar_base + 8, bar_acc1 = bar_base + 16, bar_acc2 = bar_base + 24;
+    const uint32_t tmem_slot = bar_base + 32;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    if (warp == 0 && lane == 0) { prefetch_tensormap(&mapQ); prefetch_tensormap(&mapC); }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(bar_in, 1); mbar_init(bar_c, 1); mbar_init(bar_acc1, 1); mbar_init(bar_acc2, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);                        // two 128-column accumulators
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_trigger();
+    pdl_wait();
+
+    // ---------------------------------------------------------------- 1. partial Gram block of this row tile
+    if (warp == 0 && lane == 0) {
+        mbar_arrive_expect_tx(bar_in, 4 * A_TILE_BYTES);
+        for (int kb = 0; kb < 2; ++kb) {
+            tma_load_2d(sQ + kb * A_TILE_BYTES, &mapQ, bar_in, tile * BM + kb * BK, p.q_c1);
+            tma_load_2d(sB + kb * A_TILE_BYTES, &mapQ, bar_in, tile * BM + kb * BK, p.b_c1);
+        }
+        mbar_arrive_expect_tx(bar_c, BM * 128 * 4);        // (needed in step 3 only)
+        for (int c = 0; c < 4; ++c)
+            tma_load_2d(sC + c * (BM * 32 * 4), &mapC, bar_c, tile * BM, p.b_c1 + 32 * c);
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc(0, 0u, 0u, BM, 128);      // both operands K-major
+        mbar_wait(bar_in, 0);
+        tc_fence_after_sync();
+        for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t a_desc = make_smem_desc_sw128(sQ + kb * A_TILE_BYTES, 16, 1024);
+            const uint64_t b_desc = make_smem_desc_sw128(sB + kb * A_TILE_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_f16(tmem_base, a_desc + k * (UMMA_K * 2 / 16), b_desc + k * (UMMA_K * 2 / 16), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_acc1);
+    } else if (warp >= 2) {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;                  // Q1 column = TMEM lane
+        mbar_wait(bar_acc1, 0);
+        tc_fence_after_sync();
+        float* pp = p.part + (long)tile * NODE_TILE + row;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t d[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + c * 32, d);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pp[(c * 32 + j) * 128] = __uint_as_float(d[j]);
+        }
+        tc_fence_before_sync();
+    }
+    node_grid_barrier(p.sync + 0, p.tiles);
+
+    // ---------------------------------------------------------------- 2. fixed-order sum, this CTA's share
+    {
+        const int per = (NODE_TILE + p.tiles - 1) / p.tiles;
+        const int lo = tile * per, hi = min(NODE_TILE, lo + per);
+        for (int e = lo + (int)threadIdx.x; e < hi; e += NODE_THREADS) {
+            const float* src = p.part + e;
+            float acc = 0.f;
+            int t = 0;
+            for (; t + 32 <= p.tiles; t += 32) {
+                float v[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) v[u] = __ldcg(src + (long)(t + u) * NODE_TILE);
+#pragma unroll
+                for (int u = 0; u < 32; ++u) acc += v[u];
+            }
+            for (; t < p.tiles; ++t) acc += __ldcg(src + (long)t * NODE_TILE);
+            const int i = e & 127, j = e >> 7;
+            p.R12[i + (long)j * p.ldr] = acc;
+            if (p.Z) p.Z[i + (long)j * p.ldr] = 0.f;
+            p.R12h[e] = __float2half_rn(acc);
+        }
+    }
+    node_grid_barrier(p.sync + 1, p.tiles);
+
+    // ---------------------------------------------------------------- 3. A2 tile -= Q1 tile * R12
+    // fp16 R12 -> K-major SWIZZLE_128B B operand: column n is one 128-byte row per k block, 16-byte chunk
+    // kc at position kc ^ (n & 7).  (The A2 shadow tile that lived here was consumed before barrier 1.)
+    for (int q = threadIdx.x; q < 2 * A_TILE_BYTES / 16; q += NODE_THREADS) {
+        const int n = q >> 4, kc = q & 15;
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.R12h) + q);
+        *reinterpret_cast<uint4*>(smem_gen + (sB - smem_base) + (kc >> 3) * A_TILE_BYTES + n * 128 +
+                                  (((kc & 7) ^ (n & 7)) << 4)) = v;
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc(0, 1u, 0u, BM, 128);      // A MN-major (rows), B K-major
+        tc_fence_after_sync();
+        for (int kb = 0; kb < 2; ++kb) {                   // K = Q1 columns 64 kb .. 64 kb + 63
+            // rows 0..63 of those columns sit in the first k-block tile of step 1, rows 64..127 in the second
+            const uint64_t a_desc = make_smem_desc_sw128(sQ + kb * (64 * 128), A_TILE_BYTES, 1024);
+            const uint64_t b_desc = make_smem_desc_sw128(sB + kb * A_TILE_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_f16(tmem_base + 128, a_desc + k * (UMMA_K * 128 / 16), b_desc + k * (UMMA_K * 2 / 16), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_acc2);
+    } else if (warp >= 2) {
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                    // row inside the tile = TMEM lane
+        mbar_wait(bar_c, 0);
+        mbar_wait(bar_acc2, 0);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t d[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + 128 + c * 32, d);
+            tmem_ld_wait();
+            float* sc = reinterpret_cast<float*>(smem_gen + (sC - smem_base)) + c * (BM * 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sc[j * BM + r] = sc[j * BM + r] - __uint_as_float(d[j]);
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps
+        if (warp == 2 && lane == 0) {
+            for (int c = 0; c < 4; ++c) tma_store_2d(&mapC, sC + c * (BM * 32 * 4), tile * BM, p.b_c1 + 32 * c);
+            tma_store_commit();
+            tma_store_wait<0>();
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 256);
+    }
+    if (threadIdx.x == 0) {
+        // everybody who increments this counter has passed both barriers: the last one clears them
+        if (atomicAdd(p.sync + 2, 1) == p.tiles - 1) { p.sync[0] = 0; p.sync[1] = 0; p.sync[2] = 0; }
+    }
+}
+
 template <int BN, int CCH, int CSLOTS, bool SUB, bool SHADOW>
 cudaError_t launch_u(cudaStream_t stream, int num_sms, const CUtensorMap& a, const CUtensorMap& b,
                      const CUtensorMap& c, const CUtensorMap& h, const UpdParams& p) {
@@ -393,6 +598,30 @@ cudaError_t tc_update_tma(cudaStream_t stream, int num_sms, const CUtensorMap& m
     mapH = mapC;
     return bn == 256 ? launch_u<256, 16, 2, false, false>(stream, num_sms, mapQ_64, mapB_bn, mapC, mapH, p)
                      : launch_u<128, 32, 4, false, false>(stream, num_sms, mapQ_64, mapB_bn, mapC, mapH, p);
+}
+
+bool tc_node128_supports(int num_sms, int m) { return m >= 1 && (m + BM - 1) / BM <= num_sms; }
+
+size_t tc_node128_part_floats(int m) { return (size_t)((m + BM - 1) / BM) * NODE_TILE; }
+
+cudaError_t tc_node128_init() {
+    return cudaFuncSetAttribute(tc_node128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NODE_SMEM_BYTES);
+}
+
+cudaError_t tc_node128(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int m, int colQ, int colB,
+                       float* Amat, long a_cols, long lda, float* R12, long ldr, float* Z, __half* R12h,
+                       float* part, int* sync) {
+    if (!tc_node128_supports(num_sms, m) || !part || !sync || !R12h) return cudaErrorInvalidValue;
+    NodeParams p{};
+    p.tiles = (m + BM - 1) / BM;
+    p.q_c1 = colQ; p.b_c1 = colB;
+    p.part = part; p.R12 = R12; p.ldr = ldr; p.Z = Z; p.R12h = R12h; p.sync = sync;
+    CUtensorMap mapC;
+    cudaError_t e = make_plain_map(&mapC, Amat, 4, m, a_cols, lda, BM, 32);
+    if (e != cudaSuccess) return e;
+    e = launch_pdl(tc_node128_kernel, dim3(p.tiles), dim3(NODE_THREADS), (size_t)NODE_SMEM_BYTES, stream, mapQ_128,
+                   mapC, p);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace lb
