@@ -607,7 +607,7 @@ def main():
             r_back = n * n
         else:
             # the host entry point sends back the block upper triangle of R (include/later_b200.h)
-            c = max(128, n // 16)
+            c = max(min(n, 256), n // 16)
             r_back = c * c * (n // c) * (n // c + 1) // 2
         line["e2e"] = {"value": flops / float(t_e2e.item()) / 1e12, "unit": "TFLOPS",
                        "h2d_bytes_per_step": 4 * m_loc * n * shards,
@@ -641,7 +641,7 @@ def main():
             qr.later_rgsqrf(ctx_stack, m_loc, n, A, m_loc, R, n)
             torch.cuda.synchronize()
             same_q = torch.equal(hA.cuda(), A.t())                       # every column of Q
-            c = max(128, n // 16)
+            c = max(min(n, 256), n // 16)
             blk = torch.arange(n, device="cuda") // c
             mask = blk[:, None] <= blk[None, :]                          # the block upper triangle sent back
             same_r = torch.equal(hR.cuda().t()[mask], R[mask])

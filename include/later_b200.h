@@ -71,7 +71,7 @@ int later_b200_qdwh_polar(later_b200_ctx* ctx, int n, float* X, int ldx, float* 
                           int max_iter, int* iters);
 
 /* Same with HOST buffers (what the reference's driver does by hand, test/test_qr.cu:47-56): A goes
- * to the device in column pieces of width max(128, n/16) and is factored left-looking, piece by
+ * to the device in column pieces of width max(min(n, 256), n/16) and is factored left-looking, piece by
  * piece, as it arrives; every piece of Q and its columns of R travel back the moment they are
  * final, while the factorisation continues.  hA <- Q.  hR receives its block
  * upper triangle at that granularity (strictly lower entries inside the diagonal blocks are

@@ -20,7 +20,8 @@ struct Options {
     int ormqr_kchunk = 2048;      // LB_ORMQR_KCHUNK
     bool gram_2cta = true;        // LB_GRAM_2CTA = 0: never use the CTA-pair Gram kernel
     bool peer_allreduce = true;   // LB_PEER_ALLREDUCE = 0: NCCL for every all-reduce of the row-sharded path
-    bool node_fuse = true;        // LB_NODE_FUSE = 0: 128-column nodes as three launches (Gram, reduce, update)
+    int node_fuse = 128;          // LB_NODE_FUSE: largest half-width handled by the fused node kernel (0, 128, 256;
+                                  // 256 works but measures 0.8 % slower on 16384^2)
 };
 constexpr int kSyncWords = 8;      // grid-barrier counters of the fused node kernel, behind the status words
 constexpr int kGraphSlots = 4;    // cached executable graphs per entry point (LRU)

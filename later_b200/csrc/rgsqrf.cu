@@ -100,7 +100,8 @@ Workspace plan_workspace(int num_sms, int m, int n, bool dist = false) {
         if (s > 1 && tc_gram_cast_supports(h)) s = std::max(s, tc_gram_cast_splits(num_sms, h, m));
         if (s > 1) part = std::max(part, (size_t)s * h * h * sizeof(float));
     }
-    if (n > NMIN && tc_node128_supports(num_sms, m)) part = std::max(part, tc_node128_part_floats(m) * sizeof(float));
+    for (int h = NMIN; h <= 2 * NMIN && h * 2 <= n; h *= 2)
+        if (tc_node_supports(num_sms, m, h)) part = std::max(part, tc_node_part_floats(m, h) * sizeof(float));
     w.part_bytes = part;
     w.panel_bytes = panel_scratch_bytes(m, num_sms);
     w.wh_bytes = (size_t)n * n * sizeof(__half);  // fp16 W of the TSQR back-multiplication
@@ -111,7 +112,7 @@ Workspace plan_workspace(int num_sms, int m, int n, bool dist = false) {
 }
 
 // The PCIe legs of later_b200_rgsqrf_host.  The host path runs the factorisation LEFT-LOOKING over
-// column pieces of width max(128, n/16): piece j is touched only once it has arrived, receives the
+// column pieces of width max(min(n, 256), n/16): piece j is touched only once it has arrived, receives the
 // Gram/update of every node of the recursion tree whose right half contains it (widest first - the
 // order the recursion applies them in), is then factored by the ordinary recursion, and is final.
 // Same operations on the same operands as the recursive order, so the result is bit-identical to
@@ -145,7 +146,9 @@ struct HostPipe {
         }
         return ctx->events[used++];
     }
-    static int chunk_for(int n) { return std::max(NMIN, n / 16); }
+    // (at least 256 columns, so that the nodes of half-width 128 and 256 see their whole right half in one
+    // call, as in the recursive order: those are the nodes one fused kernel handles, tc_node)
+    static int chunk_for(int n) { return std::max(std::min(n, 2 * NMIN), n / 16); }
 
     void start() {
         chunk = chunk_for(n);
@@ -286,16 +289,15 @@ struct Recursion {
     void gram_update(int c0, int h, int cb, int nb, bool zero_mirror, bool b_is_input, bool panel_next) {
         if (err != cudaSuccess) return;
         cudaStream_t st = ctx->stream;
-        // A 128-column node whose right half is factored next, on a matrix short enough for one CTA per
-        // 128-row tile: Gram product, reduce and update in one launch (tc_node128, tc_update.cu).
-        if (ctx->opts.node_fuse && h == NMIN && nb == NMIN && panel_next && !p->dist &&
-            tc_node128_supports(ctx->num_sms, p->m) && p->lda % 4 == 0 &&
-            (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
+        // A small node whose right half is factored next, on a matrix short enough for one CTA per 128-row
+        // tile: Gram product, reduce and update in one launch (tc_node, tc_update.cu).
+        if (h <= ctx->opts.node_fuse && nb == h && panel_next && !p->dist && tc_node_supports(ctx->num_sms, p->m, h) &&
+            p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->A) & 15) == 0) {
             if (b_is_input) cast(cb, cb + nb);
-            check(tc_node128(st, ctx->num_sms, q128, p->m, c0, cb, p->A, p->n, p->lda,
-                             p->R + c0 + (long)cb * p->ldr, p->ldr,
-                             zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr, p->R12h, p->part,
-                             ctx->d_info + kInfoWords));
+            check(tc_node(st, ctx->num_sms, q128, p->m, h, c0, cb, p->A, p->n, p->lda, p->Qh, p->ldh,
+                          p->R + c0 + (long)cb * p->ldr, p->ldr,
+                          zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr, p->R12h, p->part,
+                          ctx->d_info + kInfoWords));
             launches += 1;
             colmax_col = -1;
             return;
@@ -590,7 +592,7 @@ void read_options(Options& o) {
     o.ormqr_kchunk = std::max(64, geti("LB_ORMQR_KCHUNK", 2048) / 64 * 64);
     o.gram_2cta = geti("LB_GRAM_2CTA", 1) != 0;
     o.peer_allreduce = geti("LB_PEER_ALLREDUCE", 1) != 0;
-    o.node_fuse = geti("LB_NODE_FUSE", 1) != 0;
+    o.node_fuse = geti("LB_NODE_FUSE", 128);
 }
 
 std::string rank_message(const int* info) {
@@ -649,7 +651,7 @@ int later_b200_create(later_b200_ctx** out, int device, void* stream) {
     if (e == cudaSuccess) e = tc_gemm_init();
     if (e == cudaSuccess) e = tc_gram_cast_init();
     if (e == cudaSuccess) e = tc_update_init();
-    if (e == cudaSuccess) e = tc_node128_init();
+    if (e == cudaSuccess) e = tc_node_init();
     if (e == cudaSuccess) e = panel_init();
     if (e != cudaSuccess) {
         int rc = cuda_fail(ctx, e, "context setup");

@@ -109,18 +109,19 @@ cudaError_t tc_gram_cast_init();
 cudaError_t tc_gemm_init();
 cudaError_t tc_update_init();
 
-// A whole 128-column node of the recursion (R12 = Q1^T A2, A2 -= Q1 R12; Q1 = columns colQ.., A2 = columns
-// colB.. of the m-row matrix Amat / of its fp16 shadow behind mapQ_128) in one launch, one CTA per 128-row
-// tile with two grid barriers (tc_update.cu) - for m <= 128 * num_sms.  Writes R12 (fp32, ld ldr), clears the
-// mirror block Z (optional), leaves fp16 R12 in R12h (ld 128); the shadow of the new A2 is NOT written (the
-// caller factors those columns next).  part: tc_node128_part_floats(m) floats; sync: three ints, zero before
-// the first launch (the kernel leaves them zero).
-bool tc_node128_supports(int num_sms, int m);
-size_t tc_node128_part_floats(int m);
-cudaError_t tc_node128(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int m, int colQ, int colB,
-                       float* Amat, long a_cols, long lda, float* R12, long ldr, float* Z, __half* R12h,
-                       float* part, int* sync);
-cudaError_t tc_node128_init();
+// A whole small node of the recursion (half-width h = 128 or 256: R12 = Q1^T A2, A2 -= Q1 R12; Q1 = columns
+// colQ.., A2 = columns colB.. of the m-row matrix Amat / of its fp16 shadow Hmat, which mapQ_128 also covers) in
+// one launch, one CTA per 128-row tile with two grid barriers (tc_update.cu) - for m <= 128 * num_sms.  Writes
+// R12 (fp32, ld ldr), clears the mirror block Z (optional), leaves fp16 R12 in R12h (ld h); the shadow of the
+// new A2 is written from its column 128 on only (the caller factors the first 128 columns next).
+// part: tc_node_part_floats(m, h) floats; sync: three ints, zero before the first launch (the kernel leaves
+// them zero).
+bool tc_node_supports(int num_sms, int m, int h);
+size_t tc_node_part_floats(int m, int h);
+cudaError_t tc_node(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int m, int h, int colQ, int colB,
+                    float* Amat, long a_cols, long lda, __half* Hmat, long ldh, float* R12, long ldr, float* Z,
+                    __half* R12h, float* part, int* sync);
+cudaError_t tc_node_init();
 
 // Trailing update with the C tile streamed through shared memory by TMA (tc_update.cu):
 // C block = Cmat(row0:row0+Mr, c_c0:c_c0+Nc) (-)= Qh(row0:row0+Mr, colA:colA+K) * Bh(:, colB0:colB0+Nc).

@@ -337,34 +337,43 @@ cudaError_t make_plain_map(CUtensorMap* out, const void* ptr, int elem_bytes, lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// A whole 128-column node of the recursion in ONE launch, for matrices of at most 128 x #SMs rows:
-//     R12 = Q1^T A2 (128 x 128),   A2 -= Q1 R12        (Q1, A2: m x 128)
+// A whole small node of the recursion (half-width H = 128 or 256) in ONE launch, for matrices of at most
+// 128 x #SMs rows:
+//     R12 = Q1^T A2 (H x H),   A2 -= Q1 R12        (Q1, A2: m x H)
 // Separately this is a split-K Gram kernel, its reduce kernel and an update kernel - three launches with
-// a few microseconds of work each (16384 rows: 12 + 5 + 22 us under ncu for 3 us of memory time), 64 times
-// per 16384 x 16384 factorisation.  Here CTA t owns rows 128 t .. 128 t + 127 from start to end:
-//   1. TMA: its Q1 tile and the fp16 shadow of its A2 tile (K-major, 2 k blocks), and - running ahead - its
-//      fp32 A2 tile; tcgen05.mma -> partial Gram block in TMEM -> global partial t (fp32, 64 KB)
+// a few microseconds of work each (16384 rows, H = 128: 12 + 5 + 22 us under ncu for 3 us of memory time),
+// 64 + 32 times per 16384 x 16384 factorisation.  Here CTA t owns rows 128 t .. 128 t + 127 from start to end:
+//   1. TMA: its Q1 tile and the fp16 shadow of its A2 tile (K-major, 2 k blocks), and - running ahead - the
+//      fp32 A2 tile (first 128 columns); tcgen05.mma -> partial Gram block in TMEM -> global partial t (fp32)
 //   2. grid barrier; the CTAs share the fixed-order sum over the partials (t = 0, 1, ...: deterministic), CTA c
 //      taking outputs [c per, (c + 1) per): R12 to R (fp32), its zero mirror block, and the fp16 operand
-//   3. grid barrier; every CTA stages the fp16 R12 (32 KB) as the K-major B operand, and multiplies the Q1
-//      tile STILL IN SHARED MEMORY by it (the K-major tile of the Gram product is, byte for byte, the
-//      MN-major A operand of the update: one 128-byte row per matrix column); epilogue A2 - D in the staged
-//      fp32 tile, TMA store.  No fp16 shadow of the new A2: the node's right half is the next panel.
+//   3. grid barrier; per 128 columns of A2: every CTA stages the fp16 R12 columns as the K-major B operand
+//      and multiplies the Q1 tile STILL IN SHARED MEMORY by it (the K-major tile of the Gram product is, byte
+//      for byte, the MN-major A operand of the update: one 128-byte row per matrix column); epilogue A2 - D in
+//      the staged fp32 tile, TMA store.  The fp16 shadow of the new A2 is written from column 128 on only: the
+//      first 128 columns are the next panel (whose apply kernel rewrites their shadow before anybody reads it).
 // The grid barriers are counters in global memory (self-resetting: the last CTA to leave clears them); all
 // CTAs are co-resident because the grid is at most one CTA per SM and nothing before it in the stream waits
 // for it.  Spins are bounded (trap), like every other wait in this library.
 constexpr int NODE_THREADS = 192;
-constexpr int NODE_TILE = 128 * 128;                       // outputs of the node = floats per partial
-constexpr int NODE_SMEM_BYTES = 2 * A_TILE_BYTES /*Q1*/ + 2 * A_TILE_BYTES /*A2h, then R12h*/ +
-                                BM * 128 * 4 /*fp32 A2 tile*/ + 256 + 1024;
+template <int H>
+struct NodeCfg {
+    static constexpr int NQ = H / 128;                     // 128-column blocks of Q1 (M tiles of step 1) and of A2
+    static constexpr int KTILE_BYTES = H * BK * 2;         // one k block of an m x H fp16 tile: [H columns][64 rows]
+    static constexpr int C_BYTES = BM * 128 * 4;           // fp32 A2 tile, 128 columns at a time
+    static constexpr int TMEM_COLS = H == 128 ? 256 : 512; // step 1: NQ accumulators of H columns; step 3: 128
+    static constexpr int OUTPUTS = H * H;                  // floats per partial
+    static constexpr int SMEM_BYTES = 4 * KTILE_BYTES + C_BYTES + 256 + 1024;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
 
 struct NodeParams {
     int tiles;             // row tiles = gridDim.x
     int q_c1, b_c1;        // first column of Q1 / of A2 (shadow and matrix coordinates)
-    float* part;           // [tiles][128 n][128 m]
+    float* part;           // [tiles][H n][H m]
     float* R12; long ldr;  // R12 block inside R
     float* Z;              // mirror block to clear (same ld) or null
-    __half* R12h;          // fp16 R12, ld 128
+    __half* R12h;          // fp16 R12, ld H
     int* sync;             // three zero-initialised counters
 };
 
@@ -383,30 +392,37 @@ __device__ __forceinline__ void node_grid_barrier(int* counter, int target) {
     __syncthreads();
 }
 
+template <int H>
 __global__ void __launch_bounds__(NODE_THREADS, 1)
-tc_node128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapC,
-                  const NodeParams p) {
+tc_node_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapC,
+               const __grid_constant__ CUtensorMap mapH, const NodeParams p) {
+    using C = NodeCfg<H>;
+    constexpr int NQ = C::NQ;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t sQ = smem_base;                         // Q1 tile: 2 k blocks x [128 columns][64 rows] fp16
-    const uint32_t sB = sQ + 2 * A_TILE_BYTES;             // A2 shadow tile, later R12h: same shape
-    const uint32_t sC = sB + 2 * A_TILE_BYTES;             // fp32 A2 tile: 4 chunks x [32 columns][128 rows]
-    const uint32_t bar_base = sC + BM * 128 * 4;
+    const uint32_t sQ = smem_base;                         // Q1 tile: 2 k blocks x [H columns][64 rows] fp16
+    const uint32_t sB = sQ + 2 * C::KTILE_BYTES;           // A2 shadow tile; later R12h columns, new shadow
+    const uint32_t sC = sB + 2 * C::KTILE_BYTES;           // fp32 A2 tile: 4 chunks x [32 columns][128 rows]
+    const uint32_t bar_base = sC + C::C_BYTES;
     const uint32_t bar_in = bar_base, bar_c = bar_base + 8, bar_acc1 = bar_base + 16, bar_acc2 = bar_base + 24;
     const uint32_t tmem_slot = bar_base + 32;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
-    if (warp == 0 && lane == 0) { prefetch_tensormap(&mapQ); prefetch_tensormap(&mapC); }
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&mapQ);
+        prefetch_tensormap(&mapC);
+        if (NQ > 1) prefetch_tensormap(&mapH);
+    }
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(bar_in, 1); mbar_init(bar_c, 1); mbar_init(bar_acc1, 1); mbar_init(bar_acc2, 1);
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, 256);                        // two 128-column accumulators
+        tmem_alloc(tmem_slot, C::TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before_sync();
@@ -418,40 +434,47 @@ tc_node128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
 
     // ---------------------------------------------------------------- 1. partial Gram block of this row tile
     if (warp == 0 && lane == 0) {
-        mbar_arrive_expect_tx(bar_in, 4 * A_TILE_BYTES);
-        for (int kb = 0; kb < 2; ++kb) {
-            tma_load_2d(sQ + kb * A_TILE_BYTES, &mapQ, bar_in, tile * BM + kb * BK, p.q_c1);
-            tma_load_2d(sB + kb * A_TILE_BYTES, &mapQ, bar_in, tile * BM + kb * BK, p.b_c1);
-        }
-        mbar_arrive_expect_tx(bar_c, BM * 128 * 4);        // (needed in step 3 only)
+        mbar_arrive_expect_tx(bar_in, 4 * C::KTILE_BYTES);
+        for (int kb = 0; kb < 2; ++kb)
+            for (int blk = 0; blk < NQ; ++blk) {
+                tma_load_2d(sQ + kb * C::KTILE_BYTES + blk * A_TILE_BYTES, &mapQ, bar_in, tile * BM + kb * BK,
+                            p.q_c1 + blk * 128);
+                tma_load_2d(sB + kb * C::KTILE_BYTES + blk * A_TILE_BYTES, &mapQ, bar_in, tile * BM + kb * BK,
+                            p.b_c1 + blk * 128);
+            }
+        mbar_arrive_expect_tx(bar_c, C::C_BYTES);          // (needed in step 3 only)
         for (int c = 0; c < 4; ++c)
             tma_load_2d(sC + c * (BM * 32 * 4), &mapC, bar_c, tile * BM, p.b_c1 + 32 * c);
     } else if (warp == 1 && lane == 0) {
-        constexpr uint32_t idesc = make_idesc(0, 0u, 0u, BM, 128);      // both operands K-major
+        constexpr uint32_t idesc = make_idesc(0, 0u, 0u, BM, H);        // both operands K-major, N = H
         mbar_wait(bar_in, 0);
         tc_fence_after_sync();
-        for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t a_desc = make_smem_desc_sw128(sQ + kb * A_TILE_BYTES, 16, 1024);
-            const uint64_t b_desc = make_smem_desc_sw128(sB + kb * A_TILE_BYTES, 16, 1024);
+        for (int mt = 0; mt < NQ; ++mt)
+            for (int kb = 0; kb < 2; ++kb) {
+                const uint64_t a_desc = make_smem_desc_sw128(sQ + kb * C::KTILE_BYTES + mt * A_TILE_BYTES, 16, 1024);
+                const uint64_t b_desc = make_smem_desc_sw128(sB + kb * C::KTILE_BYTES, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_f16(tmem_base, a_desc + k * (UMMA_K * 2 / 16), b_desc + k * (UMMA_K * 2 / 16), idesc,
-                         (kb > 0 || k > 0) ? 1u : 0u);
-        }
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_f16(tmem_base + mt * H, a_desc + k * (UMMA_K * 2 / 16), b_desc + k * (UMMA_K * 2 / 16),
+                             idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
         umma_commit(bar_acc1);
     } else if (warp >= 2) {
         const int quad = warp & 3;
-        const int row = quad * 32 + lane;                  // Q1 column = TMEM lane
         mbar_wait(bar_acc1, 0);
         tc_fence_after_sync();
-        float* pp = p.part + (long)tile * NODE_TILE + row;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t d[32];
-            tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + c * 32, d);
-            tmem_ld_wait();
+        for (int mt = 0; mt < NQ; ++mt) {
+            // Q1 column mt 128 + quad 32 + lane = TMEM lane of accumulator mt
+            float* pp = p.part + (long)tile * C::OUTPUTS + mt * 128 + quad * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < H / 32; ++c) {
+                uint32_t d[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + mt * H + c * 32, d);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) pp[(c * 32 + j) * 128] = __uint_as_float(d[j]);
+                for (int j = 0; j < 32; ++j) pp[(c * 32 + j) * H] = __uint_as_float(d[j]);
+            }
         }
         tc_fence_before_sync();
     }
@@ -459,81 +482,133 @@ tc_node128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
 
     // ---------------------------------------------------------------- 2. fixed-order sum, this CTA's share
     {
-        const int per = (NODE_TILE + p.tiles - 1) / p.tiles;
-        const int lo = tile * per, hi = min(NODE_TILE, lo + per);
-        for (int e = lo + (int)threadIdx.x; e < hi; e += NODE_THREADS) {
-            const float* src = p.part + e;
-            float acc = 0.f;
-            int t = 0;
-            for (; t + 32 <= p.tiles; t += 32) {
-                float v[32];
+        const int per = (((C::OUTPUTS + p.tiles - 1) / p.tiles) + 3) & ~3;
+        const int lo = min(C::OUTPUTS, tile * per), hi = min(C::OUTPUTS, lo + per);
+        if constexpr (H == 128) {
+            for (int e = lo + (int)threadIdx.x; e < hi; e += NODE_THREADS) {
+                const float* src = p.part + e;
+                float acc = 0.f;
+                int t = 0;
+                for (; t + 32 <= p.tiles; t += 32) {
+                    float v[32];
 #pragma unroll
-                for (int u = 0; u < 32; ++u) v[u] = __ldcg(src + (long)(t + u) * NODE_TILE);
+                    for (int u = 0; u < 32; ++u) v[u] = __ldcg(src + (long)(t + u) * C::OUTPUTS);
 #pragma unroll
-                for (int u = 0; u < 32; ++u) acc += v[u];
+                    for (int u = 0; u < 32; ++u) acc += v[u];
+                }
+                for (; t < p.tiles; ++t) acc += __ldcg(src + (long)t * C::OUTPUTS);
+                const int i = e % H, j = e / H;
+                p.R12[i + (long)j * p.ldr] = acc;
+                if (p.Z) p.Z[i + (long)j * p.ldr] = 0.f;
+                p.R12h[e] = __float2half_rn(acc);
             }
-            for (; t < p.tiles; ++t) acc += __ldcg(src + (long)t * NODE_TILE);
-            const int i = e & 127, j = e >> 7;
-            p.R12[i + (long)j * p.ldr] = acc;
-            if (p.Z) p.Z[i + (long)j * p.ldr] = 0.f;
-            p.R12h[e] = __float2half_rn(acc);
+        } else {
+            // four consecutive outputs (same column of R12) per thread: 16-byte loads, 32 in flight
+            for (int e = lo + 4 * (int)threadIdx.x; e < hi; e += 4 * NODE_THREADS) {
+                const float4* src = reinterpret_cast<const float4*>(p.part + e);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                int t = 0;
+                for (; t + 32 <= p.tiles; t += 32) {
+                    float4 v[32];
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) v[u] = __ldcg(src + (long)(t + u) * (C::OUTPUTS / 4));
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+                }
+                for (; t < p.tiles; ++t) {
+                    const float4 v = __ldcg(src + (long)t * (C::OUTPUTS / 4));
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                const int i = e % H, j = e / H;
+                float* r = p.R12 + i + (long)j * p.ldr;
+                r[0] = acc.x; r[1] = acc.y; r[2] = acc.z; r[3] = acc.w;
+                if (p.Z) { float* z = p.Z + i + (long)j * p.ldr; z[0] = 0.f; z[1] = 0.f; z[2] = 0.f; z[3] = 0.f; }
+                const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(p.R12h + e) = pk;
+            }
         }
     }
     node_grid_barrier(p.sync + 1, p.tiles);
 
-    // ---------------------------------------------------------------- 3. A2 tile -= Q1 tile * R12
-    // fp16 R12 -> K-major SWIZZLE_128B B operand: column n is one 128-byte row per k block, 16-byte chunk
-    // kc at position kc ^ (n & 7).  (The A2 shadow tile that lived here was consumed before barrier 1.)
-    for (int q = threadIdx.x; q < 2 * A_TILE_BYTES / 16; q += NODE_THREADS) {
-        const int n = q >> 4, kc = q & 15;
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.R12h) + q);
-        *reinterpret_cast<uint4*>(smem_gen + (sB - smem_base) + (kc >> 3) * A_TILE_BYTES + n * 128 +
-                                  (((kc & 7) ^ (n & 7)) << 4)) = v;
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (warp == 1 && lane == 0) {
-        constexpr uint32_t idesc = make_idesc(0, 1u, 0u, BM, 128);      // A MN-major (rows), B K-major
-        tc_fence_after_sync();
-        for (int kb = 0; kb < 2; ++kb) {                   // K = Q1 columns 64 kb .. 64 kb + 63
-            // rows 0..63 of those columns sit in the first k-block tile of step 1, rows 64..127 in the second
-            const uint64_t a_desc = make_smem_desc_sw128(sQ + kb * (64 * 128), A_TILE_BYTES, 1024);
-            const uint64_t b_desc = make_smem_desc_sw128(sB + kb * A_TILE_BYTES, 16, 1024);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_f16(tmem_base + 128, a_desc + k * (UMMA_K * 128 / 16), b_desc + k * (UMMA_K * 2 / 16), idesc,
-                         (kb > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(bar_acc2);
-    } else if (warp >= 2) {
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;                    // row inside the tile = TMEM lane
-        mbar_wait(bar_c, 0);
-        mbar_wait(bar_acc2, 0);
-        tc_fence_after_sync();
+    // ---------------------------------------------------------------- 3. A2 tile -= Q1 tile * R12, 128 columns at a time
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t d[32];
-            tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + 128 + c * 32, d);
-            tmem_ld_wait();
-            float* sc = reinterpret_cast<float*>(smem_gen + (sC - smem_base)) + c * (BM * 32);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sc[j * BM + r] = sc[j * BM + r] - __uint_as_float(d[j]);
+    for (int np = 0; np < NQ; ++np) {
+        // fp16 R12(:, 128 np ..) -> K-major SWIZZLE_128B B operand: column n is one 128-byte row per k block,
+        // 16-byte chunk kc at position kc ^ (n & 7).  (What lived here - the A2 shadow tile, the previous
+        // pass's operand - has been consumed: barrier 1, the __syncthreads at the end of the previous pass.)
+        for (int q = threadIdx.x; q < 128 * (H / 8); q += NODE_THREADS) {
+            const int n = q / (H / 8), kc = q % (H / 8);
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.R12h + (long)(np * 128 + n) * H) + kc);
+            *reinterpret_cast<uint4*>(smem_gen + (sB - smem_base) + (kc >> 3) * A_TILE_BYTES + n * 128 +
+                                      (((kc & 7) ^ (n & 7)) << 4)) = v;
         }
-        tc_fence_before_sync();
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps
-        if (warp == 2 && lane == 0) {
-            for (int c = 0; c < 4; ++c) tma_store_2d(&mapC, sC + c * (BM * 32 * 4), tile * BM, p.b_c1 + 32 * c);
-            tma_store_commit();
-            tma_store_wait<0>();
+        __syncthreads();
+        const uint32_t acc_col = H == 128 ? 128u : uint32_t(np) * 128u;   // (step 1's accumulators are drained)
+        if (warp == 1 && lane == 0) {
+            constexpr uint32_t idesc = make_idesc(0, 1u, 0u, BM, 128);  // A MN-major (rows), B K-major
+            tc_fence_after_sync();
+            for (int kb = 0; kb < H / BK; ++kb) {          // K = Q1 columns 64 kb .. 64 kb + 63
+                // rows 0..63 of those columns sit in the first k-block tile of step 1, rows 64..127 in the second
+                const uint64_t a_desc = make_smem_desc_sw128(sQ + kb * (64 * 128), C::KTILE_BYTES, 1024);
+                const uint64_t b_desc = make_smem_desc_sw128(sB + kb * A_TILE_BYTES, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_f16(tmem_base + acc_col, a_desc + k * (UMMA_K * 128 / 16), b_desc + k * (UMMA_K * 2 / 16),
+                             idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_acc2);
+        } else if (warp >= 2) {
+            const int quad = warp & 3;
+            const int r = quad * 32 + lane;                // row inside the tile = TMEM lane
+            const bool shadow = np > 0;                    // columns 128.. of A2 are somebody's B operand later
+            mbar_wait(bar_c, np & 1);
+            mbar_wait(bar_acc2, np & 1);                   // (also: the MMAs have finished reading sB)
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t d[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc_col + c * 32, d);
+                tmem_ld_wait();
+                float* sc = reinterpret_cast<float*>(smem_gen + (sC - smem_base)) + c * (BM * 32);
+                __half* sh = reinterpret_cast<__half*>(smem_gen + (sB - smem_base)) + c * (BM * 32);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float v = sc[j * BM + r] - __uint_as_float(d[j]);
+                    sc[j * BM + r] = v;
+                    if (shadow) sh[j * BM + r] = __float2half_rn(v);
+                }
+            }
+            tc_fence_before_sync();
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory"); // the 4 epilogue warps
+            if (warp == 2 && lane == 0) {
+                const int col0 = p.b_c1 + np * 128;
+                for (int c = 0; c < 4; ++c) {
+                    tma_store_2d(&mapC, sC + c * (BM * 32 * 4), tile * BM, col0 + 32 * c);
+                    if (shadow) tma_store_2d(&mapH, sB + c * (BM * 32 * 2), tile * BM, col0 + 32 * c);
+                }
+                tma_store_commit();
+                if (np + 1 < NQ) {
+                    tma_store_wait_read<0>();              // the stores have read sC: fetch the next 128 columns
+                    mbar_arrive_expect_tx(bar_c, C::C_BYTES);
+                    for (int c = 0; c < 4; ++c)
+                        tma_load_2d(sC + c * (BM * 32 * 4), &mapC, bar_c, tile * BM, col0 + 128 + 32 * c);
+                } else {
+                    tma_store_wait<0>();
+                }
+            }
         }
+        __syncthreads();   // the pass's MMAs are complete (the epilogue waited for them): sB may be restaged
     }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
     if (threadIdx.x == 0) {
         // everybody who increments this counter has passed both barriers: the last one clears them
@@ -600,27 +675,40 @@ cudaError_t tc_update_tma(cudaStream_t stream, int num_sms, const CUtensorMap& m
                      : launch_u<128, 32, 4, false, false>(stream, num_sms, mapQ_64, mapB_bn, mapC, mapH, p);
 }
 
-bool tc_node128_supports(int num_sms, int m) { return m >= 1 && (m + BM - 1) / BM <= num_sms; }
-
-size_t tc_node128_part_floats(int m) { return (size_t)((m + BM - 1) / BM) * NODE_TILE; }
-
-cudaError_t tc_node128_init() {
-    return cudaFuncSetAttribute(tc_node128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NODE_SMEM_BYTES);
+bool tc_node_supports(int num_sms, int m, int h) {
+    return (h == 128 || h == 256) && m >= 1 && (m + BM - 1) / BM <= num_sms;
 }
 
-cudaError_t tc_node128(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int m, int colQ, int colB,
-                       float* Amat, long a_cols, long lda, float* R12, long ldr, float* Z, __half* R12h,
-                       float* part, int* sync) {
-    if (!tc_node128_supports(num_sms, m) || !part || !sync || !R12h) return cudaErrorInvalidValue;
+size_t tc_node_part_floats(int m, int h) { return (size_t)((m + BM - 1) / BM) * h * h; }
+
+cudaError_t tc_node_init() {
+    cudaError_t e = cudaFuncSetAttribute(tc_node_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         NodeCfg<128>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_node_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                NodeCfg<256>::SMEM_BYTES);
+}
+
+cudaError_t tc_node(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int m, int h, int colQ, int colB,
+                    float* Amat, long a_cols, long lda, __half* Hmat, long ldh, float* R12, long ldr, float* Z,
+                    __half* R12h, float* part, int* sync) {
+    if (!tc_node_supports(num_sms, m, h) || !part || !sync || !R12h) return cudaErrorInvalidValue;
     NodeParams p{};
     p.tiles = (m + BM - 1) / BM;
     p.q_c1 = colQ; p.b_c1 = colB;
     p.part = part; p.R12 = R12; p.ldr = ldr; p.Z = Z; p.R12h = R12h; p.sync = sync;
-    CUtensorMap mapC;
+    CUtensorMap mapC, mapH;
     cudaError_t e = make_plain_map(&mapC, Amat, 4, m, a_cols, lda, BM, 32);
     if (e != cudaSuccess) return e;
-    e = launch_pdl(tc_node128_kernel, dim3(p.tiles), dim3(NODE_THREADS), (size_t)NODE_SMEM_BYTES, stream, mapQ_128,
-                   mapC, p);
+    if (h == 256) {
+        if ((e = make_plain_map(&mapH, Hmat, 2, m, a_cols, ldh, BM, 32)) != cudaSuccess) return e;
+        e = launch_pdl(tc_node_kernel<256>, dim3(p.tiles), dim3(NODE_THREADS), (size_t)NodeCfg<256>::SMEM_BYTES,
+                       stream, mapQ_128, mapC, mapH, p);
+    } else {
+        mapH = mapC;   // (not used)
+        e = launch_pdl(tc_node_kernel<128>, dim3(p.tiles), dim3(NODE_THREADS), (size_t)NodeCfg<128>::SMEM_BYTES,
+                       stream, mapQ_128, mapC, mapH, p);
+    }
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -196,7 +196,7 @@ def later_rgsqrf_dist(ctxt: Context, m_local: int, n: int, A: torch.Tensor, lda:
 def later_rgsqrf_host(ctxt: Context | None, m: int, n: int, A: torch.Tensor, lda: int,
                       R: torch.Tensor, ldr: int) -> None:
     """Same with HOST (ideally pinned) buffers; H2D and D2H copies happen inside the call, overlapped
-    with the factorisation.  R's blocks below the block diagonal (granularity max(128, n/16)) are
+    with the factorisation.  R's blocks below the block diagonal (granularity max(min(n, 256), n/16)) are
     not written (include/later_b200.h)."""
     ctxt = ctxt or default_context()
     if A.is_cuda or R.is_cuda:

@@ -307,6 +307,39 @@ def test_cast_fused_into_gram_load_is_bit_identical(qr, m, n, monkeypatch):
     assert l1 < l0
 
 
+@pytest.mark.parametrize("m,n", [(2048, 1024), (1000, 512), (18944, 512)])
+def test_fused_node_kernel_matches_the_three_launch_path(qr, m, n, monkeypatch):
+    """Small nodes (half-width 128 by default, 256 with LB_NODE_FUSE=256) of matrices of at most 128 x #SMs
+    rows run as ONE kernel - Gram product, fixed-order reduce over the row tiles, update - instead of three
+    (tc_node_kernel, tc_update.cu).  The sums are taken over different partitions of the rows, so R agrees to
+    rounding, not bit for bit; the factorisation is as accurate either way, deterministic, and shorter."""
+    g = torch.Generator(device="cuda").manual_seed(29)
+    A0 = torch.randn(m, n, device="cuda", generator=g)
+    out = {}
+    for level in ("0", "128", "256"):
+        monkeypatch.setenv("LB_NODE_FUSE", level)
+        c = qr.Context()
+        runs = []
+        for _ in range(3):                      # direct launches, graph capture, graph replay
+            A = qr.to_colmajor(A0)
+            R = qr.colmajor_empty(n, n)
+            R.fill_(float("nan"))
+            qr.later_rgsqrf(c, m, n, A, m, R, n)
+            torch.cuda.synchronize()
+            runs.append((A, R))
+        assert all(torch.equal(runs[0][0], a) and torch.equal(runs[0][1], r) for a, r in runs[1:])
+        out[level] = (runs[0][0], runs[0][1], c.last_launch_count, qr.backward_error(A0, *runs[0]),
+                      qr.orthogonality(runs[0][0]))
+        c.close()
+    assert out["256"][2] < out["128"][2] < out["0"][2]
+    R0 = out["0"][1]
+    for level in ("128", "256"):
+        Q, R, _, back, orth = out[level]
+        assert torch.isfinite(R).all() and (torch.tril(R, -1) == 0).all()
+        assert (R - R0).norm() <= 1e-3 * R0.norm()      # (fp16 roundings downstream flip: backward-error level)
+        assert back <= 1.05 * out["0"][3] + 1e-7 and orth <= 1.05 * out["0"][4] + 1e-7
+
+
 # ------------------------------------------------------------------------------ full-size properties
 def _factor_device(qr, ctx, A0: torch.Tensor):
     m, n = A0.shape
@@ -386,8 +419,8 @@ def test_deterministic_and_graph_equals_stream(qr):
 # ------------------------------------------------------------------------------ boundary behaviour
 def _host_block_mask(n):
     """Entries of hR the host entry point writes: the block upper triangle at its transfer
-    granularity max(128, n/16) (include/later_b200.h)."""
-    c = max(128, n // 16)
+    granularity max(min(n, 256), n/16) (include/later_b200.h)."""
+    c = max(min(n, 256), n // 16)
     blk = np.arange(n) // c
     return blk[:, None] <= blk[None, :]
 
