@@ -20,6 +20,7 @@ struct Options {
     int ormqr_kchunk = 2048;      // LB_ORMQR_KCHUNK
     bool gram_2cta = true;        // LB_GRAM_2CTA = 0: never use the CTA-pair Gram kernel
     bool peer_allreduce = true;   // LB_PEER_ALLREDUCE = 0: NCCL for every all-reduce of the row-sharded path
+    bool node_coop = true;        // LB_NODE_COOP = 0: launch the fused node kernel without the cooperative attribute
     int node_fuse = 128;          // LB_NODE_FUSE: largest half-width handled by the fused node kernel (0, 128, 256;
                                   // 256 works but measures 0.8 % slower on 16384^2)
 };

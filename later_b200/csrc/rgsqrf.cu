@@ -297,7 +297,7 @@ struct Recursion {
             check(tc_node(st, ctx->num_sms, q128, p->m, h, c0, cb, p->A, p->n, p->lda, p->Qh, p->ldh,
                           p->R + c0 + (long)cb * p->ldr, p->ldr,
                           zero_mirror ? p->R + cb + (long)c0 * p->ldr : nullptr, p->R12h, p->part,
-                          ctx->d_info + kInfoWords));
+                          ctx->d_info + kInfoWords, ctx->opts.node_coop));
             launches += 1;
             colmax_col = -1;
             return;
@@ -593,6 +593,7 @@ void read_options(Options& o) {
     o.gram_2cta = geti("LB_GRAM_2CTA", 1) != 0;
     o.peer_allreduce = geti("LB_PEER_ALLREDUCE", 1) != 0;
     o.node_fuse = geti("LB_NODE_FUSE", 128);
+    o.node_coop = geti("LB_NODE_COOP", 1) != 0;
 }
 
 std::string rank_message(const int* info) {

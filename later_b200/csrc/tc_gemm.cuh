@@ -120,8 +120,12 @@ bool tc_node_supports(int num_sms, int m, int h);
 size_t tc_node_part_floats(int m, int h);
 cudaError_t tc_node(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int m, int h, int colQ, int colB,
                     float* Amat, long a_cols, long lda, __half* Hmat, long ldh, float* R12, long ldr, float* Z,
-                    __half* R12h, float* part, int* sync);
+                    __half* R12h, float* part, int* sync, bool cooperative);
 cudaError_t tc_node_init();
+// cooperative = launch with the cooperative attribute on top of programmatic dependent launch (co-residency of
+// the grid guaranteed by the driver); falls back to the plain launch, once and for all, if the driver rejects the
+// combination.  tc_node_cooperative_state(): 0 untried, 1 accepted, -1 rejected.
+int tc_node_cooperative_state();
 
 // Trailing update with the C tile streamed through shared memory by TMA (tc_update.cu):
 // C block = Cmat(row0:row0+Mr, c_c0:c_c0+Nc) (-)= Qh(row0:row0+Mr, colA:colA+K) * Bh(:, colB0:colB0+Nc).

@@ -15,6 +15,8 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdio>
 
 namespace lb {
 
@@ -689,9 +691,34 @@ cudaError_t tc_node_init() {
                                 NodeCfg<256>::SMEM_BYTES);
 }
 
+namespace {
+// Programmatic dependent launch plus, if asked for, the cooperative attribute: the driver then guarantees that
+// all CTAs of the grid are resident together (and keeps two such grids on one device from starving each other).
+template <int H>
+cudaError_t launch_node(int grid, cudaStream_t stream, bool cooperative, const CUtensorMap& q, const CUtensorMap& c,
+                        const CUtensorMap& h, const NodeParams& p) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NODE_THREADS);
+    cfg.dynamicSmemBytes = (size_t)NodeCfg<H>::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cooperative ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, tc_node_kernel<H>, q, c, h, p);
+}
+std::atomic<int> g_node_coop{0};   // 0 = untried, 1 = the driver takes cooperative + PDL launches, -1 = it does not
+}  // namespace
+
+int tc_node_cooperative_state() { return g_node_coop.load(); }
+
 cudaError_t tc_node(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_128, int m, int h, int colQ, int colB,
                     float* Amat, long a_cols, long lda, __half* Hmat, long ldh, float* R12, long ldr, float* Z,
-                    __half* R12h, float* part, int* sync) {
+                    __half* R12h, float* part, int* sync, bool cooperative) {
     if (!tc_node_supports(num_sms, m, h) || !part || !sync || !R12h) return cudaErrorInvalidValue;
     NodeParams p{};
     p.tiles = (m + BM - 1) / BM;
@@ -702,12 +729,31 @@ cudaError_t tc_node(cudaStream_t stream, int num_sms, const CUtensorMap& mapQ_12
     if (e != cudaSuccess) return e;
     if (h == 256) {
         if ((e = make_plain_map(&mapH, Hmat, 2, m, a_cols, ldh, BM, 32)) != cudaSuccess) return e;
-        e = launch_pdl(tc_node_kernel<256>, dim3(p.tiles), dim3(NODE_THREADS), (size_t)NodeCfg<256>::SMEM_BYTES,
-                       stream, mapQ_128, mapC, mapH, p);
     } else {
         mapH = mapC;   // (not used)
-        e = launch_pdl(tc_node_kernel<128>, dim3(p.tiles), dim3(NODE_THREADS), (size_t)NodeCfg<128>::SMEM_BYTES,
-                       stream, mapQ_128, mapC, mapH, p);
+    }
+    auto launch = [&](bool coop) {
+        return h == 256 ? launch_node<256>(p.tiles, stream, coop, mapQ_128, mapC, mapH, p)
+                        : launch_node<128>(p.tiles, stream, coop, mapQ_128, mapC, mapH, p);
+    };
+    // The first cooperative launch of the process is never made inside a stream capture (a rejected launch
+    // would invalidate the capture): until the driver has accepted one, captures use the plain launch.
+    bool coop = cooperative && g_node_coop.load() >= 0;
+    if (coop && g_node_coop.load() == 0) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) coop = false;
+    }
+    e = launch(coop);
+    if (coop) {
+        if (e == cudaSuccess) {
+            g_node_coop.store(1);
+        } else {               // not launched: remember, clear the error, launch the plain way
+            (void)cudaGetLastError();
+            if (g_node_coop.exchange(-1) != -1)
+                fprintf(stderr, "later_b200: cooperative launch of the fused node kernel rejected (%s); using plain launches\n",
+                        cudaGetErrorString(e));
+            e = launch(false);
+        }
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }
