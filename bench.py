@@ -454,7 +454,7 @@ def main():
         "data": f"synthetic N(0,1): counter-based generator keyed by the global element index, seed {SEED} "
                 "(a row shard equals those rows of the single-GPU matrix)",
         "config": {"workload": workload, "m": m, "n": n, "parallelism": f"dp{N}" if N > 1 else "single",
-                   "l2": "inputs (>= 1 GiB) exceed the 126 MB L2; no flush needed",
+                   "l2": f"inputs ({m_loc * n * 4 / 2 ** 20:.0f} MiB per GPU) exceed the 126 MB L2; no flush needed",
                    "timing": "CUDA events around each factorisation, max over ranks; input restore outside"},
         "step_ms": step_ms, "wall_ms_per_step_incl_restore": t_wall * 1e3 / args.steps,
         "executed_tflops": 2.0 * m * n * n / (ms_per_step * 1e-3) / 1e12,
