@@ -1,5 +1,7 @@
-"""Host-side logic of the row-sharded TSQR (later_b200/tsqr.py) on CPU: world_size 2, gloo backend,
-with the numpy oracle standing in for the CUDA kernels through tsqr_rgsqrf's injection points."""
+"""The N > 1 paths on CPU, world_size 2, gloo backend: the host-side logic of the row-sharded TSQR
+(later_b200/tsqr.py) with the numpy oracle standing in for the CUDA kernels through tsqr_rgsqrf's injection
+points, and the algorithm of the row-sharded recursion (later_b200_rgsqrf_dist) as a numpy model with its
+two kinds of all-reduce going through torch.distributed."""
 import os
 import sys
 from pathlib import Path
@@ -66,6 +68,53 @@ def test_tsqr_two_ranks_gloo(tmp_path):
     # same factor as a single-process factorisation of the whole matrix, up to rounding
     _, Rref = orc.later_rgsqrf(A)
     assert np.abs(R0 - Rref).max() <= 5e-3 * np.abs(Rref).max()
+
+
+def _sharded_worker(rank, world, port, m, n, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.helpers.sharded_model import rgsqrf_sharded
+    calls = {"f64": 0, "f32": 0}
+
+    def allreduce(x):
+        calls["f64" if x.dtype == np.float64 else "f32"] += 1
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    A_glob = np.random.default_rng(22).standard_normal((m, n), dtype=np.float32)
+    mloc = m // world
+    Q, R = rgsqrf_sharded(A_glob[rank * mloc:(rank + 1) * mloc], allreduce)
+    np.save(os.path.join(tmp, f"q{rank}.npy"), Q)
+    np.save(os.path.join(tmp, f"r{rank}.npy"), R)
+    np.save(os.path.join(tmp, f"calls{rank}.npy"), np.array([calls["f64"], calls["f32"]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_recursion_two_ranks_gloo(tmp_path):
+    """What later_b200_rgsqrf_dist promises: one fp64 all-reduce per panel and one fp32
+    all-reduce per node, the same R on every rank bit for bit, and the accuracy of the unsharded factorisation
+    (the TSQR variant rounds Q to fp16 once more and is 50x worse)."""
+    from oracle import rgsqrf_oracle as orc
+    from tests.helpers.sharded_model import rgsqrf_sharded
+    m, n, world = 2048, 512, 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_sharded_worker, args=(world, port, m, n, str(tmp_path)), nprocs=world, join=True)
+    Q = np.concatenate([np.load(tmp_path / f"q{r}.npy") for r in range(world)], axis=0)
+    R0, R1 = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
+    assert np.array_equal(R0, R1)
+    assert np.load(tmp_path / "calls0.npy").tolist() == [n // 128, n // 128 - 1]     # panels, nodes
+    A = np.random.default_rng(22).standard_normal((m, n), dtype=np.float32)
+    assert np.abs(np.tril(R0, -1)).max() == 0 and (np.diag(R0) > 0).all()
+    Q1, R1p = rgsqrf_sharded(A)                        # one rank: no exchange at all
+    back1, orth1 = orc.check_result(A, Q1, R1p), orc.check_otho(Q1)
+    back, orth = orc.check_result(A, Q, R0), orc.check_otho(Q)
+    assert back <= 1.1 * back1 and orth <= 1.1 * orth1
+    assert np.abs(R0 - R1p).max() <= 1e-3 * np.abs(R1p).max()
+    # ... which is the accuracy of the reference's algorithm on the same matrix (oracle, fp32 MGS panels)
+    Qo, Ro = orc.later_rgsqrf(A)
+    assert back <= 2 * orc.check_result(A, Qo, Ro) and orth <= 2 * orc.check_otho(Qo)
 
 
 def test_stack_layout():
